@@ -1,0 +1,1385 @@
+// ipt_oracle.cpp -- CPU ORACLE (test infrastructure, NOT product code).
+//
+// A from-scratch C++17 restatement of the reference renderer's algorithm
+// (bblinn2017/inverse_path_tracer).  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library; the product
+// (inverse_path_tracer_b200/) never links, imports or executes anything under oracle/.
+//
+// What pins it (DESIGN.md section "Oracle"):
+//   * loader tables        <- the reference's own tiny_obj_loader.h/material.h/utils.h compiled
+//                             from /root/reference by oracle/Makefile into oracle/_ref/ (tests
+//                             compare vertex bits, triangle order and per-face materials)
+//   * forward integrator   <- the reference's only known-answer output preds/0_true.png
+//                             (statistical: region means + RMSE, tests/golden/golden_0_true.*)
+//   * Philox4x32-10        <- Random123 known-answer vectors
+//   * createGraph          <- PARITY UNPINNED: the reference ships no output for it (data.pt is
+//                             missing, mat.npy is stale); only structural invariants are tested
+//   * material gradients   <- PARITY UNPINNED: no gradient exists in the reference; checked
+//                             against central finite differences of this oracle's own renderer
+//
+// The reference cannot be compiled here (needs Eigen, stb_image, managed CUDA memory at load
+// time), and nvcc's FMA contraction makes its exact rounding unknowable, so THIS FILE DEFINES
+// THE CANONICAL FP32 OPERATION ORDER ("canon").  Every arithmetic step is
+// spelled out with explicit fmaf()/+/*; compile with -ffp-contract=off so nothing else fuses.
+// The CUDA product implements the same canon independently (different data layout, precomputed
+// edge planes, SoA) and must match this file bit for bit on hit ids, t, and rendered images.
+//
+// Each function cites the reference file:line it follows (paths relative to the reference root).
+
+#include <algorithm>
+#include <atomic>
+#include <cerrno>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace orc {
+
+// ----------------------------------------------------------------------------------------------
+// canon vector math (replaces Eigen::Vector3f; scene_basics.h:22-28)
+// ----------------------------------------------------------------------------------------------
+struct V3 {
+  float x, y, z;
+};
+static inline V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+static inline V3 add(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline V3 sub(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline V3 scale(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+static inline V3 neg(V3 a) { return mk(-a.x, -a.y, -a.z); }
+// dot: ((ax*bx) + ay*by) + az*bz with the two additions fused
+static inline float dot(V3 a, V3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+static inline V3 cross(V3 a, V3 b) {
+  return mk(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+// Eigen normalize(): z = squaredNorm; if (z > 0) v /= sqrt(z).  canon: one IEEE division, 3 products.
+static inline V3 normalize(V3 v) {
+  float z = dot(v, v);
+  if (z > 0.0f) {
+    float inv = 1.0f / sqrtf(z);
+    return scale(v, inv);
+  }
+  return v;
+}
+static inline float norm(V3 v) { return sqrtf(dot(v, v)); }
+static inline float comp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+
+static const float kPi = 3.14159274f;        // (float)M_PI
+static const float kInvPi = 0.318309873f;    // (float)(1./M_PI)  (path_trace.cu:108)
+static const float kMinDot = 1e-4f;          // |denom| <  1e-4 (double)  <=>  |denom| <= 1e-4f
+static const float kEpsT = 1e-2f;            //   t     <  1e-2 (double)  <=>    t     <= 1e-2f
+
+// ----------------------------------------------------------------------------------------------
+// Philox4x32-10 counter RNG (replaces cuRAND XORWOW, path_trace.cu:151-153).  Key = 64-bit seed,
+// counter = (pixel, sample, bounce, stream).  Known answers: Random123 kat_vectors.
+// ----------------------------------------------------------------------------------------------
+static inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+  uint32_t k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// curand_uniform maps a 32-bit draw to (0,1]:  x*2^-32 + 2^-33  (curand_uniform.h); canon fuses it.
+static inline float u01(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+enum { STREAM_CAMERA = 0, STREAM_NEE_RR = 1, STREAM_DIR = 2 };
+struct Rng {
+  uint32_t key[2];
+  uint32_t pixel, sample;
+  void draw(uint32_t bounce, uint32_t stream, float u[4]) const {
+    uint32_t ctr[4] = {pixel, sample, bounce, stream}, o[4];
+    philox4x32_10(ctr, key, o);
+    for (int i = 0; i < 4; i++) u[i] = u01(o[i]);
+  }
+};
+
+// sin/cos of 2*pi*u with exact quadrant reduction and fixed polynomials (canon; replaces the
+// device sin()/cos() of phi = 2*M_PI*u, path_trace.cu:93,96).  Only + * fma -> same bits anywhere.
+static inline void sincos2pi(float u, float* s_out, float* c_out) {
+  float a = 4.0f * u;                 // exact
+  float qf = floorf(a + 0.5f);
+  float r = a - qf;                   // exact, in [-0.5, 0.5]
+  int q = ((int)qf) & 3;
+  float z = r * r;
+  // sin(pi/2 * r) = r * (S0 + z*(S1 + z*(S2 + z*(S3 + z*S4))))
+  float sp = fmaf(z, 1.60441181e-04f, -4.68175393e-03f);
+  sp = fmaf(z, sp, 7.96926245e-02f);
+  sp = fmaf(z, sp, -6.45964086e-01f);
+  sp = fmaf(z, sp, 1.57079637e+00f);
+  float s = r * sp;
+  // cos(pi/2 * r) = 1 + z*(C1 + z*(C2 + z*(C3 + z*(C4 + z*C5))))
+  float cp = fmaf(z, -2.52020418e-05f, 9.19260259e-04f);
+  cp = fmaf(z, cp, -2.08634809e-02f);
+  cp = fmaf(z, cp, 2.53669500e-01f);
+  cp = fmaf(z, cp, -1.23370051e+00f);
+  float c = fmaf(z, cp, 1.0f);
+  switch (q) {
+    case 0: *s_out = s; *c_out = c; break;
+    case 1: *s_out = c; *c_out = -s; break;
+    case 2: *s_out = -s; *c_out = -c; break;
+    default: *s_out = -c; *c_out = s; break;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// number / OBJ / MTL parsing.  Restates the grammar of the reference's trimmed tinyobjloader:
+// utils.h:70-200 (tryParseDouble: digit-by-digit double accumulation, then cast to float),
+// tiny_obj_loader.h:585-933 (LoadObj), :179-583 (exportGroupsToShape: quad split rule),
+// material.h:380-780 (LoadMtl).
+// ----------------------------------------------------------------------------------------------
+static inline bool is_space(char c) { return c == ' ' || c == '\t'; }
+static inline bool is_digit(char c) { return (unsigned)(c - '0') < 10u; }
+
+// utils.h:70-200
+static bool parse_double(const char* s, const char* s_end, double* result) {
+  if (s >= s_end) return false;
+  double mantissa = 0.0;
+  int exponent = 0;
+  char sign = '+', exp_sign = '+';
+  const char* curr = s;
+  int read = 0;
+  bool end_not_reached = false, leading_dot = false;
+  if (*curr == '+' || *curr == '-') {
+    sign = *curr;
+    curr++;
+    if (curr != s_end && *curr == '.') leading_dot = true;
+  } else if (is_digit(*curr)) {
+  } else if (*curr == '.') {
+    leading_dot = true;
+  } else {
+    return false;
+  }
+  end_not_reached = (curr != s_end);
+  if (!leading_dot) {
+    while (end_not_reached && is_digit(*curr)) {
+      mantissa *= 10;
+      mantissa += (int)(*curr - '0');
+      curr++; read++;
+      end_not_reached = (curr != s_end);
+    }
+    if (read == 0) return false;
+  }
+  if (end_not_reached) {
+    bool has_exp = false;
+    if (*curr == '.') {
+      curr++;
+      read = 1;
+      end_not_reached = (curr != s_end);
+      static const double lut[] = {1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001};
+      while (end_not_reached && is_digit(*curr)) {
+        mantissa += (int)(*curr - '0') * (read < 8 ? lut[read] : std::pow(10.0, -read));
+        read++; curr++;
+        end_not_reached = (curr != s_end);
+      }
+      has_exp = end_not_reached && (*curr == 'e' || *curr == 'E');
+    } else if (*curr == 'e' || *curr == 'E') {
+      has_exp = true;
+    }
+    if (has_exp) {
+      curr++;
+      end_not_reached = (curr != s_end);
+      if (end_not_reached && (*curr == '+' || *curr == '-')) {
+        exp_sign = *curr;
+        curr++;
+      } else if (end_not_reached && is_digit(*curr)) {
+      } else {
+        return false;
+      }
+      read = 0;
+      end_not_reached = (curr != s_end);
+      while (end_not_reached && is_digit(*curr)) {
+        if (exponent > 2147483647 / 10) return false;
+        exponent = exponent * 10 + (int)(*curr - '0');
+        curr++; read++;
+        end_not_reached = (curr != s_end);
+      }
+      exponent *= (exp_sign == '+' ? 1 : -1);
+      if (read == 0) return false;
+    }
+  }
+  *result = (sign == '+' ? 1 : -1) * (exponent ? std::ldexp(mantissa * std::pow(5.0, exponent), exponent) : mantissa);
+  return true;
+}
+// utils.h:202-210 (parseReal with default 0)
+static float parse_real(const char** tok) {
+  *tok += strspn(*tok, " \t");
+  const char* end = *tok + strcspn(*tok, " \t\r");
+  double v = 0.0;
+  parse_double(*tok, end, &v);
+  *tok = end;
+  return (float)v;
+}
+static void parse_real3(float* x, float* y, float* z, const char** tok) {
+  *x = parse_real(tok); *y = parse_real(tok); *z = parse_real(tok);
+}
+
+// mat_t (scene_basics.h:35-62) / material_t defaults (material.h:341-351)
+struct Material {
+  float kd[3] = {0, 0, 0}, ks[3] = {0, 0, 0}, kt[3] = {0, 0, 0}, ke[3] = {0, 0, 0};
+  float ns = 1.0f, ni = 1.0f, d = 1.0f;
+  int illum = 0;
+  std::string name;
+};
+
+// material.h:380-780; only the fields mat_t copies are kept (scene_basics.h:50-59)
+static void load_mtl(std::istream& in, std::vector<Material>* mats, std::map<std::string, int>* mat_map) {
+  Material m;
+  bool has_d = false, has_tr = false;
+  std::string line;
+  while (std::getline(in, line)) {
+    size_t last = line.find_last_not_of(" \t\r\n");
+    line = (last == std::string::npos) ? std::string() : line.substr(0, last + 1);
+    if (line.empty()) continue;
+    const char* tok = line.c_str();
+    tok += strspn(tok, " \t");
+    if (tok[0] == '\0' || tok[0] == '#') continue;
+    if (0 == strncmp(tok, "newmtl", 6) && is_space(tok[6])) {
+      if (!m.name.empty()) {
+        mat_map->insert(std::make_pair(m.name, (int)mats->size()));
+        mats->push_back(m);
+      }
+      m = Material();
+      has_d = has_tr = false;
+      m.name = std::string(tok + 7);
+      continue;
+    }
+    if (tok[0] == 'K' && tok[1] == 'd' && is_space(tok[2])) { tok += 2; parse_real3(&m.kd[0], &m.kd[1], &m.kd[2], &tok); continue; }
+    if (tok[0] == 'K' && tok[1] == 's' && is_space(tok[2])) { tok += 2; parse_real3(&m.ks[0], &m.ks[1], &m.ks[2], &tok); continue; }
+    if (tok[0] == 'K' && tok[1] == 'e' && is_space(tok[2])) { tok += 2; parse_real3(&m.ke[0], &m.ke[1], &m.ke[2], &tok); continue; }
+    if ((tok[0] == 'K' && tok[1] == 't' && is_space(tok[2])) || (tok[0] == 'T' && tok[1] == 'f' && is_space(tok[2]))) {
+      tok += 2; parse_real3(&m.kt[0], &m.kt[1], &m.kt[2], &tok); continue;
+    }
+    if (tok[0] == 'N' && tok[1] == 'i' && is_space(tok[2])) { tok += 2; m.ni = parse_real(&tok); continue; }
+    if (tok[0] == 'N' && tok[1] == 's' && is_space(tok[2])) { tok += 2; m.ns = parse_real(&tok); continue; }
+    if (0 == strncmp(tok, "illum", 5) && is_space(tok[5])) { tok += 6; tok += strspn(tok, " \t"); m.illum = atoi(tok); continue; }
+    if (tok[0] == 'd' && is_space(tok[1])) { tok += 1; m.d = parse_real(&tok); has_d = true; continue; }
+    if (tok[0] == 'T' && tok[1] == 'r' && is_space(tok[2])) {
+      tok += 2;
+      if (!has_d) m.d = 1.0f - parse_real(&tok);
+      has_tr = true;
+      continue;
+    }
+    // everything else (Ka, maps, PBR extensions) is never read by the renderer
+  }
+  (void)has_tr;
+  mat_map->insert(std::make_pair(m.name, (int)mats->size()));
+  mats->push_back(m);  // material.h flushes the last material unconditionally
+}
+
+struct ObjData {
+  std::vector<float> v, vn;         // xyz triples
+  std::vector<int> face_v;          // 3 vertex indices per triangle, in reference triangle order
+  std::vector<int> face_mat;        // material id per triangle (-1 = none)
+  std::vector<Material> materials;  // from the MTL stream
+};
+
+// tiny_obj_loader.h:288-309 (fixIndex) + :311-362 (parseTriple); only v_idx matters downstream
+// because scene_basics.h:274-276 keeps vertex_index only.
+static bool parse_face_vertex(const char** tok, int vsize, int* v_idx) {
+  int idx = atoi(*tok);
+  if (idx > 0) *v_idx = idx - 1;
+  else if (idx < 0) *v_idx = vsize + idx;
+  else return false;
+  *tok += strcspn(*tok, " \t\r");  // skip the /vt/vn part
+  return true;
+}
+
+static bool load_obj(const std::string& obj_path, const std::string& mtl_arg, ObjData* out, std::string* err) {
+  std::ifstream in(obj_path.c_str());
+  if (!in) { *err = "cannot open OBJ file '" + obj_path + "': " + strerror(errno); return false; }
+  const bool inline_mtl = !mtl_arg.empty() && mtl_arg[0] == '*';  // scene_basics.h:223
+  std::map<std::string, int> mat_map;
+  int material = -1;
+  struct Face { std::vector<int> vi; int mat; };
+  std::vector<Face> faces;
+  std::string line;
+  bool mtl_consumed = false;
+  while (std::getline(in, line)) {
+    while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
+    if (line.empty()) continue;
+    const char* tok = line.c_str();
+    tok += strspn(tok, " \t");
+    if (tok[0] == '\0' || tok[0] == '#') continue;
+    if (tok[0] == 'v' && is_space(tok[1])) {
+      tok += 2;
+      float x, y, z;
+      parse_real3(&x, &y, &z, &tok);
+      out->v.push_back(x); out->v.push_back(y); out->v.push_back(z);
+      continue;
+    }
+    if (tok[0] == 'v' && tok[1] == 'n' && is_space(tok[2])) {
+      tok += 3;
+      float x, y, z;
+      parse_real3(&x, &y, &z, &tok);
+      out->vn.push_back(x); out->vn.push_back(y); out->vn.push_back(z);
+      continue;
+    }
+    if (tok[0] == 'f' && is_space(tok[1])) {
+      tok += 2;
+      tok += strspn(tok, " \t");
+      Face f;
+      f.mat = material;
+      while (tok[0] != '\0' && tok[0] != '\r' && tok[0] != '\n') {
+        int vi;
+        if (!parse_face_vertex(&tok, (int)(out->v.size() / 3), &vi)) { *err = "bad face index in " + obj_path; return false; }
+        f.vi.push_back(vi);
+        tok += strspn(tok, " \t\r");
+      }
+      faces.push_back(f);
+      continue;
+    }
+    if (0 == strncmp(tok, "usemtl", 6)) {
+      tok += 6;
+      tok += strspn(tok, " \t");
+      std::string name(tok, strcspn(tok, " \t\r"));
+      std::map<std::string, int>::const_iterator it = mat_map.find(name);
+      material = (it != mat_map.end()) ? it->second : -1;
+      continue;
+    }
+    if (0 == strncmp(tok, "mtllib", 6) && is_space(tok[6])) {
+      // The reference ignores the file name and reads the MTL stream it was given
+      // (MaterialStreamReader, material.h:784-809; scene_basics.h:224-225).
+      if (!inline_mtl && !mtl_consumed) {
+        std::ifstream mtl(mtl_arg.c_str());
+        if (mtl) load_mtl(mtl, &out->materials, &mat_map);
+        mtl_consumed = true;
+      }
+      continue;
+    }
+    // g / o / s / vt: no effect on triangle order or materials (shapes are concatenated in
+    // file order by scene_basics.h:270-286)
+  }
+  // triangulate (tiny_obj_loader.h:204-308 for quads).  The quad rule: compare the squared
+  // diagonals |v2-v0|^2 < |v3-v1|^2 -> [0,1,2],[0,2,3] else [0,1,3],[1,2,3]  (plain float ops,
+  // left-to-right sums, no fma: host code of the reference is compiled by the host compiler).
+  const std::vector<float>& v = out->v;
+  for (size_t i = 0; i < faces.size(); i++) {
+    const Face& f = faces[i];
+    size_t n = f.vi.size();
+    if (n < 3) continue;
+    if (n == 3) {
+      out->face_v.insert(out->face_v.end(), {f.vi[0], f.vi[1], f.vi[2]});
+      out->face_mat.push_back(f.mat);
+    } else if (n == 4) {
+      bool ok = true;
+      for (int k = 0; k < 4; k++) ok = ok && ((size_t)(3 * f.vi[k] + 2) < v.size()) && f.vi[k] >= 0;
+      if (!ok) continue;
+      const float* p0 = &v[3 * f.vi[0]]; const float* p1 = &v[3 * f.vi[1]];
+      const float* p2 = &v[3 * f.vi[2]]; const float* p3 = &v[3 * f.vi[3]];
+      float e02x = p2[0] - p0[0], e02y = p2[1] - p0[1], e02z = p2[2] - p0[2];
+      float e13x = p3[0] - p1[0], e13y = p3[1] - p1[1], e13z = p3[2] - p1[2];
+      float sqr02 = e02x * e02x + e02y * e02y + e02z * e02z;
+      float sqr13 = e13x * e13x + e13y * e13y + e13z * e13z;
+      if (sqr02 < sqr13) {
+        out->face_v.insert(out->face_v.end(), {f.vi[0], f.vi[1], f.vi[2], f.vi[0], f.vi[2], f.vi[3]});
+      } else {
+        out->face_v.insert(out->face_v.end(), {f.vi[0], f.vi[1], f.vi[3], f.vi[1], f.vi[2], f.vi[3]});
+      }
+      out->face_mat.push_back(f.mat);
+      out->face_mat.push_back(f.mat);
+    } else {
+      // n-gons (> 4): the reference ear-clips (tiny_obj_loader.h:310-564); no shipped asset has
+      // one.  DEVIATION: fan triangulation.
+      for (size_t k = 1; k + 1 < n; k++) {
+        out->face_v.insert(out->face_v.end(), {f.vi[0], f.vi[k], f.vi[k + 1]});
+        out->face_mat.push_back(f.mat);
+      }
+    }
+  }
+  return true;
+}
+
+// ----------------------------------------------------------------------------------------------
+// scene types: Triangle (scene_basics.h:64-110), Object (:402-517), Camera/Scene (scene.h:35-173)
+// ----------------------------------------------------------------------------------------------
+struct Triangle {
+  int idx = 0, idxE = -1;
+  Material mat;
+  V3 v[3];
+  V3 vn[3];
+  bool has_vn = false;
+  V3 normal, center;
+  float area = 0;
+};
+
+// scene_basics.h:74-96
+static Triangle make_triangle(int i, const Material& m, const V3 vs[3], const V3* ns) {
+  Triangle t;
+  t.idx = i;
+  t.mat = m;
+  V3 c = mk(0, 0, 0);
+  for (int j = 0; j < 3; j++) {
+    t.v[j] = vs[j];
+    c = add(c, mk(vs[j].x / 3.0f, vs[j].y / 3.0f, vs[j].z / 3.0f));
+  }
+  t.center = c;
+  V3 a = sub(t.v[1], t.v[0]);
+  V3 b = sub(t.v[2], t.v[1]);
+  V3 n = cross(a, b);
+  t.area = norm(n) / 2.0f;
+  t.normal = normalize(n);
+  t.has_vn = ns != nullptr;
+  for (int j = 0; j < 3; j++) t.vn[j] = ns ? ns[j] : t.normal;
+  return t;
+}
+
+// scene_basics.h:100-109.  canon: triangles without per-vertex normals return the face normal
+// itself (the barycentric blend of three identical normals is the same direction; the reference
+// recomputes it and lands within an ulp).
+static V3 shading_normal(const Triangle& t, V3 p) {
+  if (!t.has_vn) return t.normal;
+  float w[3];
+  for (int i = 0; i < 3; i++) {
+    V3 c = cross(sub(t.v[(i + 1) % 3], p), sub(t.v[(i + 2) % 3], p));
+    w[i] = (0.5f * norm(c)) / t.area;
+  }
+  V3 n = mk(fmaf(t.vn[2].x, w[2], fmaf(t.vn[1].x, w[1], t.vn[0].x * w[0])),
+            fmaf(t.vn[2].y, w[2], fmaf(t.vn[1].y, w[1], t.vn[0].y * w[0])),
+            fmaf(t.vn[2].z, w[2], fmaf(t.vn[1].z, w[1], t.vn[0].z * w[0])));
+  return normalize(n);
+}
+
+struct Ray { V3 p, d; };
+struct Hit {
+  float t = INFINITY;
+  V3 point = {0, 0, 0};
+  int tri = -1;  // global triangle index (reference: Triangle*)
+};
+
+struct Box { V3 lo, hi; };
+static inline V3 vmin(V3 a, V3 b) { return mk(std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z)); }
+static inline V3 vmax(V3 a, V3 b) { return mk(std::max(a.x, b.x), std::max(a.y, b.y), std::max(a.z, b.z)); }
+
+// Affine transform (scene_basics.h:147-157): T = Translate(pos) * AngleAxis(|ori|, ori/|ori|) * Scale(scl)
+struct Affine {
+  float L[3][3];
+  V3 t;
+};
+static Affine make_transform(V3 pos, V3 ori, V3 scl) {
+  Affine T;
+  float angle = norm(ori);
+  V3 ax = normalize(ori);
+  // Eigen AngleAxis::toRotationMatrix
+  float s = sinf(angle), c = cosf(angle);
+  V3 sin_axis = scale(ax, s);
+  V3 cos1_axis = scale(ax, 1.0f - c);
+  float R[3][3];
+  float tmp;
+  tmp = cos1_axis.x * ax.y; R[0][1] = tmp - sin_axis.z; R[1][0] = tmp + sin_axis.z;
+  tmp = cos1_axis.x * ax.z; R[0][2] = tmp + sin_axis.y; R[2][0] = tmp - sin_axis.y;
+  tmp = cos1_axis.y * ax.z; R[1][2] = tmp - sin_axis.x; R[2][1] = tmp + sin_axis.x;
+  R[0][0] = fmaf(cos1_axis.x, ax.x, c);
+  R[1][1] = fmaf(cos1_axis.y, ax.y, c);
+  R[2][2] = fmaf(cos1_axis.z, ax.z, c);
+  float sc[3] = {scl.x, scl.y, scl.z};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) T.L[i][j] = R[i][j] * sc[j];
+  T.t = pos;
+  return T;
+}
+static V3 xform_point(const Affine& T, V3 v) {
+  return mk(dot(mk(T.L[0][0], T.L[0][1], T.L[0][2]), v) + T.t.x,
+            dot(mk(T.L[1][0], T.L[1][1], T.L[1][2]), v) + T.t.y,
+            dot(mk(T.L[2][0], T.L[2][1], T.L[2][2]), v) + T.t.z);
+}
+// normals transform with (L^T)^-1 (scene_basics.h:240-243); cofactor inverse, computed in double
+// then rounded (host-only, both implementations run this on the CPU).
+static void normal_matrix(const Affine& T, float N[3][3]) {
+  double a[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] = T.L[j][i];  // transpose
+  double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+               a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+  double inv[3][3];
+  inv[0][0] = (a[1][1] * a[2][2] - a[1][2] * a[2][1]) / det;
+  inv[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) / det;
+  inv[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) / det;
+  inv[1][0] = (a[1][2] * a[2][0] - a[1][0] * a[2][2]) / det;
+  inv[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) / det;
+  inv[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) / det;
+  inv[2][0] = (a[1][0] * a[2][1] - a[1][1] * a[2][0]) / det;
+  inv[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) / det;
+  inv[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) / det;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) N[i][j] = (float)inv[i][j];
+}
+
+struct Object {
+  std::vector<Triangle> tris;
+  V3 pos;
+  Box bbox;
+
+  // Object::signedDistance, scene_basics.h:497-503 (recomputed per call like the reference)
+  static float signed_distance(V3 point, V3 s0, V3 s1, V3 normal) {
+    V3 out = normalize(cross(sub(s1, s0), normal));
+    float d = (-dot(out, add(s1, s0))) / 2.0f;
+    return fmaf(point.z, out.z, fmaf(point.y, out.y, fmaf(point.x, out.x, d)));
+  }
+
+  // Object::getIntersection, scene_basics.h:426-459
+  void intersect(const Ray& ray, Hit& best) const {
+    for (size_t i = 0; i < tris.size(); i++) {
+      const Triangle& tri = tris[i];
+      float denom = dot(tri.normal, ray.d);
+      if (fabsf(denom) <= kMinDot) continue;                 // abs(denom) < MIN_DOT (double 1e-4)
+      // t = (p - c).n / -denom, canon:  (c.n - n.p) / denom
+      float t = (dot(tri.center, tri.normal) - dot(tri.normal, ray.p)) / denom;
+      if (!(t > kEpsT) || !(t < best.t)) continue;          // t < EPSILON || t >= best.t
+      V3 point = mk(fmaf(ray.d.x, t, ray.p.x), fmaf(ray.d.y, t, ray.p.y), fmaf(ray.d.z, t, ray.p.z));
+      bool has_int = true;
+      for (int j = 0; j < 3; j++) {
+        float sd = signed_distance(point, tri.v[j], tri.v[(j + 1) % 3], tri.normal);
+        if (sd > 0.0f) { has_int = false; break; }
+      }
+      if (!has_int) continue;
+      best.t = t;
+      best.point = point;
+      best.tri = tri.idx;
+    }
+  }
+};
+
+// ----------------------------------------------------------------------------------------------
+// BVH::build, bvh.h:109-205, over a generic primitive array (boxes + split positions).
+// The reference runs it over Objects (position = obj.pos); the product reuses the same algorithm
+// with triangles as primitives (position = triangle center).  Fixed vs the reference: `parent`
+// is an int (bvh.h:14 uses char and breaks past 127 nodes), the work stack is a real vector
+// (bvh.h:116-124 indexes a reserved-but-empty vector).
+// ----------------------------------------------------------------------------------------------
+struct FlatNode {
+  float lo[3], hi[3];
+  int start, nPrims, rightOffset;
+};
+static void bvh_build(const Box* boxes, const V3* pos, int n, int leaf_size, std::vector<FlatNode>* nodes,
+                      std::vector<int>* perm) {
+  nodes->clear();
+  perm->resize(n);
+  for (int i = 0; i < n; i++) (*perm)[i] = i;
+  if (n == 0) return;
+  struct Entry { int parent, start, end; };
+  std::vector<Entry> todo;
+  todo.push_back(Entry{-4, 0, n});  // 0xfffffffc
+  const int UNTOUCHED = -1, TOUCHED_TWICE = -3;
+  std::vector<int>& p = *perm;
+  while (!todo.empty()) {
+    Entry e = todo.back();
+    todo.pop_back();
+    int start = e.start, end = e.end, nPrims = end - start;
+    FlatNode node;
+    node.start = start;
+    node.nPrims = nPrims;
+    node.rightOffset = UNTOUCHED;
+    Box bb = boxes[p[start]];
+    V3 clo = pos[p[start]], chi = pos[p[start]];
+    for (int q = start + 1; q < end; q++) {
+      bb.lo = vmin(bb.lo, boxes[p[q]].lo);
+      bb.hi = vmax(bb.hi, boxes[p[q]].hi);
+      clo = vmin(clo, pos[p[q]]);
+      chi = vmax(chi, pos[p[q]]);
+    }
+    node.lo[0] = bb.lo.x; node.lo[1] = bb.lo.y; node.lo[2] = bb.lo.z;
+    node.hi[0] = bb.hi.x; node.hi[1] = bb.hi.y; node.hi[2] = bb.hi.z;
+    if (nPrims <= leaf_size) node.rightOffset = 0;
+    nodes->push_back(node);
+    int me = (int)nodes->size() - 1;
+    if (e.parent != -4) {
+      FlatNode& par = (*nodes)[e.parent];
+      par.rightOffset -= 1;
+      if (par.rightOffset == TOUCHED_TWICE) par.rightOffset = me - e.parent;
+    }
+    if (node.rightOffset == 0) continue;
+    // bbox_t::maxDimension, scene_basics.h:359-369: strict > starting from 0 -> lowest axis on ties
+    V3 ext = sub(chi, clo);
+    int dim = 0;
+    float mx = 0.0f;
+    for (int i = 0; i < 3; i++) if (comp(ext, i) > mx) { mx = comp(ext, i); dim = i; }
+    float split = (comp(clo, dim) + comp(chi, dim)) / 2.0f;
+    int mid = start;
+    for (int i = start; i < end; i++) {
+      if (comp(pos[p[i]], dim) < split) {
+        std::swap(p[i], p[mid]);
+        mid++;
+      }
+    }
+    if (mid == start || mid == end) mid = start + (end - start) / 2;
+    todo.push_back(Entry{me, mid, end});
+    todo.push_back(Entry{me, start, mid});
+  }
+}
+
+// Camera::getInverseViewMatrix, scene.h:49-77 ("inverse view" = scale * view^T)
+struct Camera {
+  float M[4][4];
+};
+static Camera make_camera(const float eye[3], const float look[3], const float up[3], float height_angle_deg, float aspect) {
+  V3 pos = mk(eye[0], eye[1], eye[2]);
+  V3 f = normalize(normalize(mk(look[0], look[1], look[2])));
+  V3 upn = normalize(mk(up[0], up[1], up[2]));
+  V3 s = normalize(cross(f, upn));
+  V3 u = normalize(cross(s, f));
+  float ha = (float)(M_PI * (double)height_angle_deg / 360.0);   // scene.h:43
+  float view[4][4] = {{s.x, s.y, s.z, -dot(s, pos)}, {u.x, u.y, u.z, -dot(u, pos)}, {f.x, f.y, f.z, -dot(f, pos)}, {0, 0, 0, 1}};
+  float sc[4] = {tanf(ha), tanf(ha * aspect), 1.0f, 1.0f};
+  Camera cam;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) cam.M[i][j] = sc[i] * view[j][i];  // scale * view^T
+  return cam;
+}
+
+struct Scene {
+  std::vector<Object> objects;
+  std::vector<std::pair<int, int>> tri_ref;   // global idx -> (object, local)
+  std::vector<int> emissives;                 // global triangle idx per emissive (scene.h:100-114)
+  std::vector<float> light_cdf;               // running sums of area_i/area_sum (path_trace.cu:44-50)
+  float area_sum = 0;
+  Camera cam;
+  int nT = 0;
+  std::string error;
+
+  const Triangle& tri(int idx) const { return objects[tri_ref[idx].first].tris[tri_ref[idx].second]; }
+  Triangle& tri(int idx) { return objects[tri_ref[idx].first].tris[tri_ref[idx].second]; }
+
+  // Scene::getIntersection -> BVH::getIntersection (bvh.h:37-107) in the only regime where the
+  // reference is correct (<= 4 objects = one leaf): objects in order, fresh `curr` per object,
+  // kept iff curr.t < best.t (strict => first object wins ties).  SURVEY.md R2: for > 4 objects
+  // the parity target is this same true closest hit with lowest (object, triangle) order at ties.
+  Hit closest_hit(const Ray& ray) const {
+    Hit best;
+    for (size_t o = 0; o < objects.size(); o++) {
+      Hit curr;
+      objects[o].intersect(ray, curr);
+      if (curr.tri >= 0 && curr.t < best.t) best = curr;
+    }
+    return best;
+  }
+
+  void finalize_lights() {
+    emissives.clear();
+    for (int i = 0; i < nT; i++) {
+      Triangle& t = tri(i);
+      t.idxE = -1;
+      if (t.mat.ke[0] > 0.0f || t.mat.ke[1] > 0.0f || t.mat.ke[2] > 0.0f) {
+        t.idxE = (int)emissives.size();
+        emissives.push_back(i);
+      }
+    }
+    area_sum = 0.0f;
+    for (int e : emissives) area_sum += tri(e).area;     // path_trace.cu:39-42
+    light_cdf.clear();
+    float p_curr = 0.0f;
+    for (int e : emissives) { p_curr += tri(e).area / area_sum; light_cdf.push_back(p_curr); }
+  }
+};
+
+// Mesh ctor + ParseFromString (scene_basics.h:147-194, 207-289), Object ctor (:405-413),
+// Scene ctor (scene.h:89-117), loadScene (scene.h:177-193)
+static Scene* load_scene(const float* poss, const float* oris, const float* scls, const char* const* objs,
+                         const char* const* mtls, int n, const char* root, std::string* err) {
+  Scene* sc = new Scene();
+  std::string r = root ? std::string(root) : std::string();
+  auto resolve = [&](const std::string& p) {
+    if (r.empty() || p.empty() || p[0] == '/') return p;
+    return r + "/" + p;
+  };
+  for (int o = 0; o < n; o++) {
+    V3 pos = mk(poss[3 * o], poss[3 * o + 1], poss[3 * o + 2]);
+    V3 ori = mk(oris[3 * o], oris[3 * o + 1], oris[3 * o + 2]);
+    V3 scl = mk(scls[3 * o], scls[3 * o + 1], scls[3 * o + 2]);
+    Affine T = make_transform(pos, ori, scl);
+    std::string mtl_arg = mtls[o];
+    bool inline_mtl = !mtl_arg.empty() && mtl_arg[0] == '*';
+    ObjData od;
+    if (!load_obj(resolve(objs[o]), inline_mtl ? mtl_arg : resolve(mtl_arg), &od, err)) { delete sc; return nullptr; }
+    // inline material "*Kd r g b*" (scene_basics.h:249-268): only Kd is honoured
+    Material rand_mat;
+    if (inline_mtl && mtl_arg.size() >= 2) {
+      std::stringstream ss(mtl_arg.substr(1, mtl_arg.size() - 2));
+      std::string line;
+      while (std::getline(ss, line, '\n')) {
+        const char* tok = line.c_str();
+        if (line.size() >= 3 && tok[0] == 'K' && is_space(tok[2])) {
+          char k = tok[1];
+          tok += 2;
+          float rr, gg, bb;
+          parse_real3(&rr, &gg, &bb, &tok);
+          if (k == 'd') { rand_mat.kd[0] = rr; rand_mat.kd[1] = gg; rand_mat.kd[2] = bb; }
+        }
+      }
+    }
+    std::vector<V3> vs, ns;
+    for (size_t i = 0; i < od.v.size() / 3; i++) vs.push_back(xform_point(T, mk(od.v[3 * i], od.v[3 * i + 1], od.v[3 * i + 2])));
+    float N[3][3];
+    normal_matrix(T, N);
+    for (size_t i = 0; i < od.vn.size() / 3; i++) {
+      V3 nn = mk(od.vn[3 * i], od.vn[3 * i + 1], od.vn[3 * i + 2]);
+      ns.push_back(mk(dot(mk(N[0][0], N[0][1], N[0][2]), nn), dot(mk(N[1][0], N[1][1], N[1][2]), nn), dot(mk(N[2][0], N[2][1], N[2][2]), nn)));
+    }
+    Object obj;
+    obj.pos = pos;
+    obj.bbox.lo = obj.bbox.hi = pos;   // bbox_t::setP(obj.pos), scene_basics.h:407
+    size_t nF = od.face_v.size() / 3;
+    for (size_t i = 0; i < nF; i++) {
+      int f0 = od.face_v[3 * i], f1 = od.face_v[3 * i + 1], f2 = od.face_v[3 * i + 2];
+      if (f0 < 0 || f1 < 0 || f2 < 0 || (size_t)f0 >= vs.size() || (size_t)f1 >= vs.size() || (size_t)f2 >= vs.size()) {
+        *err = std::string("face references a missing vertex in ") + objs[o];
+        delete sc;
+        return nullptr;
+      }
+      V3 tv[3] = {vs[f0], vs[f1], vs[f2]};
+      V3 tn[3];
+      const V3* tnp = nullptr;
+      if (ns.size() == vs.size()) {      // scene_basics.h:176 -- normals indexed by VERTEX index
+        tn[0] = ns[f0]; tn[1] = ns[f1]; tn[2] = ns[f2];
+        tnp = tn;
+      }
+      int mid = od.face_mat[i];
+      const Material& m = (mid != -1) ? od.materials[mid] : rand_mat;
+      obj.tris.push_back(make_triangle((int)i, m, tv, tnp));
+      for (int j = 0; j < 3; j++) { obj.bbox.lo = vmin(obj.bbox.lo, tv[j]); obj.bbox.hi = vmax(obj.bbox.hi, tv[j]); }
+    }
+    sc->objects.push_back(obj);
+  }
+  // Scene ctor: global offsets (scene_basics.h:467-474)
+  int nT = 0;
+  for (size_t o = 0; o < sc->objects.size(); o++) {
+    for (size_t i = 0; i < sc->objects[o].tris.size(); i++) {
+      sc->objects[o].tris[i].idx += nT;
+      sc->tri_ref.push_back(std::make_pair((int)o, (int)i));
+    }
+    nT += (int)sc->objects[o].tris.size();
+  }
+  sc->nT = nT;
+  sc->finalize_lights();
+  const float eye[3] = {0, 0, 0}, look[3] = {0, 0, 1}, up[3] = {0, 1, 0};   // scene.h:3-7
+  sc->cam = make_camera(eye, look, up, 90.0f, 1.0f);
+  return sc;
+}
+
+// ----------------------------------------------------------------------------------------------
+// integrator (path_trace.cu)
+// ----------------------------------------------------------------------------------------------
+struct Params {
+  int width, height, spp, max_depth;   // max_depth <= 0: unbounded (reference behaviour)
+  float p_rr;                          // scene.h:11 (.9f)
+  uint32_t seed_lo, seed_hi;
+  int group_samples;                   // samples summed sequentially per partial (<=0: spp)
+  int row_begin, row_end;              // rows rendered [begin,end) (pixel-row sharding)
+};
+
+struct Counters {
+  uint64_t paths = 0, ext_rays = 0, shadow_rays = 0;
+};
+
+// rotation taking +z to N: Eigen::Quaternionf::FromTwoVectors((0,0,1), N).matrix() specialised to
+// a = z (path_trace.cu:98-103); N.z == -1 handled by the caller.
+static void frame_from_z(V3 N, float R[3][3]) {
+  float c = N.z;   // a.b with a = (0,0,1)
+  float qx, qy, qw;
+  if (c < -1.0f + 1e-5f) {
+    // Eigen falls back to an SVD here; canon: half-turn-like rotation about normalize(z x N)
+    float w2 = (1.0f + c) * 0.5f;
+    V3 ax = normalize(mk(-N.y, N.x, 0.0f));
+    if (ax.x == 0.0f && ax.y == 0.0f) ax = mk(1.0f, 0.0f, 0.0f);
+    float sv = sqrtf(1.0f - w2);
+    qx = ax.x * sv; qy = ax.y * sv; qw = sqrtf(w2);
+  } else {
+    float s = sqrtf((1.0f + c) * 2.0f);
+    float invs = 1.0f / s;
+    qx = -N.y * invs; qy = N.x * invs; qw = s * 0.5f;
+  }
+  // Eigen quaternion -> matrix with qz = 0
+  float tx = 2.0f * qx, ty = 2.0f * qy;
+  float twx = tx * qw, twy = ty * qw;
+  float txx = tx * qx, txy = ty * qx, tyy = ty * qy;
+  R[0][0] = 1.0f - tyy; R[0][1] = txy;        R[0][2] = twy;
+  R[1][0] = txy;        R[1][1] = 1.0f - txx; R[1][2] = -twx;
+  R[2][0] = -twy;       R[2][1] = twx;        R[2][2] = 1.0f - (txx + tyy);
+}
+
+// sampleNextDir, path_trace.cu:91-109 (identical in inv_path_trace.cu:89-107)
+static float sample_next_dir(V3 normDir, bool isSpecular, float shininess, float u_phi, float u_theta, V3* nextDir) {
+  float sphi, cphi;
+  sincos2pi(u_phi, &sphi, &cphi);
+  float cth, sth;
+  if (isSpecular) {
+    cth = powf(u_theta, 1.0f / (shininess + 1.0f));
+    sth = sqrtf(fmaxf(0.0f, 1.0f - cth * cth));
+  } else {
+    cth = sqrtf(u_theta);            // cos(acos(sqrt(u)))
+    sth = sqrtf(1.0f - u_theta);     // sin(acos(sqrt(u)))
+  }
+  V3 hemi = mk(sth * cphi, sth * sphi, cth);
+  V3 nd;
+  if (normDir.z == -1.0f) {
+    nd = neg(hemi);
+  } else {
+    float R[3][3];
+    frame_from_z(normDir, R);
+    nd = mk(dot(mk(R[0][0], R[0][1], R[0][2]), hemi), dot(mk(R[1][0], R[1][1], R[1][2]), hemi), dot(mk(R[2][0], R[2][1], R[2][2]), hemi));
+  }
+  *nextDir = normalize(nd);
+  return isSpecular ? powf((shininess + 1.0f) * cth, shininess) : kInvPi;
+}
+
+static inline bool has_specular(const Material& m) { return (m.ks[0] != 0.0f || m.ks[1] != 0.0f || m.ks[2] != 0.0f); }
+
+// BSDF, path_trace.cu:10-28 (diagonal of the 3x3).  The Phong lobe is skipped when Ks == 0
+// (0 * finite = 0 exactly; NaN from pow(negative, non-integer) is squashed by max(NaN,0) = 0).
+static void bsdf(const Triangle& tri, V3 hit, V3 w, V3 w_i, bool isDirect, float out[3]) {
+  for (int i = 0; i < 3; i++) out[i] = isDirect ? tri.mat.kd[i] : tri.mat.kd[i] / kPi;
+  if (has_specular(tri.mat)) {
+    float n = tri.mat.ns;
+    V3 nrm = shading_normal(tri, hit);
+    float k = 2.0f * dot(nrm, w_i);
+    V3 refl = mk(fmaf(k, nrm.x, -w_i.x), fmaf(k, nrm.y, -w_i.y), fmaf(k, nrm.z, -w_i.z));
+    float pw = powf(dot(refl, w), n);
+    float coeff = ((n + 2.0f) / 2.0f / kPi) * fmaxf(pw, 0.0f);
+    for (int i = 0; i < 3; i++) out[i] = fmaf(tri.mat.ks[i], coeff, out[i]);
+  }
+}
+
+// light sampling shared by directLighting in both integrators (path_trace.cu:30-81,
+// inv_path_trace.cu:16-65).  Returns false on any of the reference's early-outs.
+struct LightSample {
+  int light_tri;
+  float cos_theta, cos_theta_prime, t, p_t;
+  V3 toLight;
+};
+static bool sample_light(const Scene& sc, const Hit& isect, const float u[3], LightSample* ls, Counters* cnt) {
+  int nE = (int)sc.emissives.size();
+  int idx = 0;
+  while (idx < nE - 1 && !(sc.light_cdf[idx] >= u[0])) idx++;   // clamp: reference reads out of bounds
+  const Triangle& t_emm = sc.tri(sc.emissives[idx]);
+  ls->light_tri = t_emm.idx;
+  ls->p_t = t_emm.area / sc.area_sum;
+  float s = sqrtf(u[1]);
+  float c1 = 1.0f - s, c2 = s * (1.0f - u[2]), c3 = u[2] * s;
+  V3 ep = mk(fmaf(c3, t_emm.v[2].x, fmaf(c2, t_emm.v[1].x, c1 * t_emm.v[0].x)),
+             fmaf(c3, t_emm.v[2].y, fmaf(c2, t_emm.v[1].y, c1 * t_emm.v[0].y)),
+             fmaf(c3, t_emm.v[2].z, fmaf(c2, t_emm.v[1].z, c1 * t_emm.v[0].z)));
+  V3 toLight = normalize(sub(ep, isect.point));
+  ls->toLight = toLight;
+  const Triangle& t_curr = sc.tri(isect.tri);
+  ls->cos_theta = dot(shading_normal(t_curr, isect.point), toLight);
+  if (ls->cos_theta < 0.0f) return false;
+  Ray lr{isect.point, toLight};
+  Hit i = sc.closest_hit(lr);
+  cnt->shadow_rays++;
+  if (i.tri < 0) return false;
+  ls->cos_theta_prime = -dot(shading_normal(t_emm, i.point), toLight);
+  if (ls->cos_theta_prime < 0.0f) return false;
+  if (i.tri != t_emm.idx) return false;
+  ls->t = i.t;
+  return true;
+}
+
+// camera ray, path_trace.cu:155-165 + Ray::transform scene_basics.h:307-319
+static Ray camera_ray(const Scene& sc, const Params& P, int r, int c, float ux, float uy) {
+  float x = (2.0f * ((float)c + ux)) / (float)P.width - 1.0f;
+  float y = 1.0f - (2.0f * ((float)r + uy)) / (float)P.height;
+  V3 d = normalize(mk(x, y, 1.0f));
+  V3 p = mk(0, 0, 0);
+  const float(*M)[4] = sc.cam.M;
+  Ray ray;
+  ray.p = mk(dot(mk(M[0][0], M[0][1], M[0][2]), p) + M[0][3], dot(mk(M[1][0], M[1][1], M[1][2]), p) + M[1][3],
+             dot(mk(M[2][0], M[2][1], M[2][2]), p) + M[2][3]);
+  ray.d = normalize(mk(dot(mk(M[0][0], M[0][1], M[0][2]), d), dot(mk(M[1][0], M[1][1], M[1][2]), d), dot(mk(M[2][0], M[2][1], M[2][2]), d)));
+  return ray;
+}
+
+// one path vertex record for the adjoint sweep (new functionality)
+struct Vertex {
+  int tri;          // triangle hit at this iteration (-1: miss)
+  int light;        // sampled light triangle when the NEE connection was visible, else -1
+  float g;          // cos*cos'/t^2/p_t of the visible connection (0 otherwise)
+  float b;          // throughput factor excluding Kd: (1/pi) * coeff (0 when the path stopped here)
+  bool cont;        // path continued past this vertex
+};
+
+// renderSample + radiance, path_trace.cu:111-184.  Returns L of one pixel sample.  `trace`
+// (optional) receives the vertex list for the adjoint.
+static void render_sample(const Scene& sc, const Params& P, int r, int c, int sample, float L[3], Counters* cnt,
+                          std::vector<Vertex>* trace) {
+  Rng rng;
+  rng.key[0] = P.seed_lo; rng.key[1] = P.seed_hi;
+  rng.pixel = (uint32_t)(r * P.width + c);
+  rng.sample = (uint32_t)sample;
+  float u[4];
+  rng.draw(0, STREAM_CAMERA, u);
+  Ray ray = camera_ray(sc, P, r, c, u[0], u[1]);
+  L[0] = L[1] = L[2] = 0.0f;
+  float L_e[3] = {0, 0, 0}, L_d[3] = {0, 0, 0};
+  float mult[3] = {1, 1, 1}, prev[3] = {1, 1, 1};
+  int recursion = 0;
+  bool recur = true;
+  cnt->paths++;
+  const int nE = (int)sc.emissives.size();
+  while (recur) {
+    // ---- radiance() ----
+    Vertex vx{-1, -1, 0.0f, 0.0f, false};
+    Hit isect = sc.closest_hit(ray);
+    cnt->ext_rays++;
+    recur = false;
+    if (isect.tri >= 0) {
+      const Triangle& tri = sc.tri(isect.tri);
+      vx.tri = tri.idx;
+      if (recursion == 0) for (int i = 0; i < 3; i++) L_e[i] = tri.mat.ke[i];
+      // directLighting, path_trace.cu:30-89
+      float un[4];
+      rng.draw((uint32_t)recursion, STREAM_NEE_RR, un);
+      L_d[0] = L_d[1] = L_d[2] = 0.0f;
+      if (nE > 0) {
+        LightSample ls;
+        if (sample_light(sc, isect, un, &ls, cnt)) {
+          float g = ((ls.cos_theta * ls.cos_theta_prime) / (ls.t * ls.t)) / ls.p_t;
+          const Triangle& t_emm = sc.tri(ls.light_tri);
+          float f[3];
+          bsdf(tri, isect.point, ray.d, ls.toLight, true, f);
+          for (int i = 0; i < 3; i++) L_d[i] = f[i] * (t_emm.mat.ke[i] * g);
+          vx.light = ls.light_tri;
+          vx.g = g;
+        }
+      }
+      // Russian roulette + continuation, path_trace.cu:130-141
+      if (un[3] < P.p_rr) {
+        float ud[4];
+        rng.draw((uint32_t)recursion, STREAM_DIR, ud);
+        bool isSpecular = has_specular(tri.mat) && tri.mat.ns != 0.0f;
+        V3 nextDir;
+        float p_sample = sample_next_dir(tri.normal, isSpecular, tri.mat.ns, ud[0], ud[1], &nextDir);
+        float f[3];
+        bsdf(tri, isect.point, ray.d, nextDir, false, f);
+        float coeff = (dot(nextDir, shading_normal(tri, isect.point)) / p_sample) / P.p_rr;
+        for (int i = 0; i < 3; i++) mult[i] = (mult[i] * f[i]) * coeff;
+        vx.b = coeff / kPi;   // bookkeeping for the adjoint only (diffuse materials)
+        vx.cont = true;
+        ray.p = isect.point;
+        ray.d = nextDir;
+        recur = true;
+      }
+    }
+    // ---- back in renderSample ----
+    for (int i = 0; i < 3; i++) L[i] = fmaf(prev[i], L_e[i] + L_d[i], L[i]);
+    for (int i = 0; i < 3; i++) prev[i] = mult[i];
+    recursion++;
+    if (P.max_depth > 0 && recursion >= P.max_depth) { recur = false; vx.cont = false; }
+    if (trace) trace->push_back(vx);
+  }
+}
+
+static inline int group_size(const Params& P) { return (P.group_samples <= 0 || P.group_samples > P.spp) ? P.spp : P.group_samples; }
+
+// pixel mean: toneMap's sum  sum_i src[i]/SPP  (path_trace.cu:190-193), in groups of
+// `group_samples` consecutive samples; group partials are then added in group order.
+static void render_pixel(const Scene& sc, const Params& P, int r, int c, float out[3], Counters* cnt) {
+  const int gs = group_size(P);
+  float total[3] = {0, 0, 0};
+  for (int g0 = 0; g0 < P.spp; g0 += gs) {
+    float part[3] = {0, 0, 0};
+    for (int s = g0; s < std::min(P.spp, g0 + gs); s++) {
+      float L[3];
+      render_sample(sc, P, r, c, s, L, cnt, nullptr);
+      for (int i = 0; i < 3; i++) part[i] += L[i] / (float)P.spp;
+    }
+    if (g0 == 0) for (int i = 0; i < 3; i++) total[i] = part[i];
+    else for (int i = 0; i < 3; i++) total[i] += part[i];
+  }
+  for (int i = 0; i < 3; i++) out[i] = total[i];
+}
+
+template <class F>
+static void parallel_rows(int r0, int r1, int threads, F fn) {
+  if (threads <= 1) { for (int r = r0; r < r1; r++) fn(r, 0); return; }
+  std::atomic<int> next(r0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++)
+    pool.emplace_back([&, t]() { for (;;) { int r = next.fetch_add(1); if (r >= r1) break; fn(r, t); } });
+  for (auto& th : pool) th.join();
+}
+
+// toneMap, path_trace.cu:195-197
+static inline uint8_t tonemap_u8(float v) { return (uint8_t)(255.0f * v / (1.0f + v)); }
+
+// ----------------------------------------------------------------------------------------------
+// inverse pass: Edge / DataWrapper (inv_scene.h:9-115), radiance (inv_path_trace.cu:109-150)
+// Accumulators are double (the reference adds floats atomically in arbitrary order).
+// ----------------------------------------------------------------------------------------------
+struct Edge {
+  long long n = 0;
+  double w_sum = 0, pixel_sum[2][3] = {{0, 0, 0}, {0, 0, 0}}, light_sum[2][3] = {{0, 0, 0}, {0, 0, 0}}, factors_sum[2] = {0, 0};
+  void update(float w, const float pixel[3], const float light[3], const float factors[2]) {   // inv_scene.h:26-36
+    n += 1;
+    w_sum += w;
+    for (int j = 0; j < 2; j++) {
+      float wf = w * factors[j];
+      for (int i = 0; i < 3; i++) { pixel_sum[j][i] += wf * pixel[i]; light_sum[j][i] += wf * light[i]; }
+      factors_sum[j] += wf;
+    }
+  }
+  void merge(const Edge& o) {
+    n += o.n; w_sum += o.w_sum;
+    for (int j = 0; j < 2; j++) { for (int i = 0; i < 3; i++) { pixel_sum[j][i] += o.pixel_sum[j][i]; light_sum[j][i] += o.light_sum[j][i]; } factors_sum[j] += o.factors_sum[j]; }
+  }
+};
+
+static const float kPSpec = 0.0f;   // inv_scene.h:5
+
+static void graph_sample(const Scene& sc, const Params& P, int r, int c, int sample, const float pixel[3], std::vector<Edge>& edges, Counters* cnt) {
+  const int nT = sc.nT;
+  Rng rng;
+  rng.key[0] = P.seed_lo; rng.key[1] = P.seed_hi;
+  rng.pixel = (uint32_t)(r * P.width + c);
+  rng.sample = (uint32_t)sample;
+  float u[4];
+  rng.draw(0, STREAM_CAMERA, u);
+  Ray ray = camera_ray(sc, P, r, c, u[0], u[1]);
+  float weight = 1.0f;
+  float factors[2] = {1.0f, 1.0f};
+  int recursion = 0;
+  int dst = nT;   // eye row (inv_path_trace.cu:177)
+  const float zero[3] = {0, 0, 0};
+  const int nE = (int)sc.emissives.size();
+  // 1/p_sample/p_RR/(1-P_SPEC) evaluated in double like the reference, then rounded (inv_path_trace.cu:145)
+  const float wscale = (float)(1.0 / (double)kInvPi / (double)P.p_rr / (1.0 - (double)kPSpec));
+  cnt->paths++;
+  while (dst != -1) {
+    Hit isect = sc.closest_hit(ray);
+    cnt->ext_rays++;
+    if (isect.tri < 0) break;
+    const Triangle& tri = sc.tri(isect.tri);
+    float un[4], ud[4];
+    rng.draw((uint32_t)recursion, STREAM_NEE_RR, un);
+    rng.draw((uint32_t)recursion, STREAM_DIR, ud);
+    bool isSpecular = ud[2] < kPSpec;   // always false
+    int src = tri.idx;
+    edges[(size_t)dst * nT + src].update(weight, pixel, zero, factors);
+    if (nE > 0) {
+      LightSample ls;
+      if (sample_light(sc, isect, un, &ls, cnt)) {
+        float w = (((weight * ls.cos_theta) * ls.cos_theta_prime) / (ls.t * ls.t)) / ls.p_t;
+        float f[2] = {kInvPi, 0.0f};   // BSDF(isDirect=true), inv_path_trace.cu:8,13
+        edges[(size_t)tri.idx * nT + ls.light_tri].update(w, pixel, sc.tri(ls.light_tri).mat.ke, f);
+      }
+    }
+    if (!(un[3] < P.p_rr)) break;
+    V3 nextDir;
+    sample_next_dir(tri.normal, isSpecular, 0.0f, ud[0], ud[1], &nextDir);
+    factors[0] = 1.0f; factors[1] = 0.0f;   // BSDF(isDirect=false)
+    weight = weight * dot(nextDir, shading_normal(tri, isect.point));
+    weight = weight * wscale;
+    ray.p = isect.point;
+    ray.d = nextDir;
+    dst = src;
+    recursion++;
+    if (P.max_depth > 0 && recursion >= P.max_depth) break;
+  }
+}
+
+// DataWrapper::compress + Edge::normalize, inv_scene.h:38-47, 87-115
+static void graph_compress(const std::vector<Edge>& edges, int nT, float* data) {
+  size_t size = (size_t)(nT + 1) * nT;
+  float* weights = data;
+  float* pixels = data + size;
+  float* lights = data + size * 4;
+  for (int dst = 0; dst <= nT; dst++) {
+    // output row order: dst = 0..nT-1 then the eye row (DataWrapper::get maps dst == nT to eyeEdges)
+    float w_total = 0.0f;
+    std::vector<float> wrow(nT);
+    for (int src = 0; src < nT; src++) {
+      const Edge& e = edges[(size_t)dst * nT + src];
+      float w = logf((float)e.w_sum + 1.0f);
+      float div = ((float)e.factors_sum[0] != 0.0f) ? (float)e.factors_sum[0] : 1.0f;
+      wrow[src] = w;
+      w_total += w;
+      for (int i = 0; i < 3; i++) {
+        pixels[((size_t)dst * nT + src) * 3 + i] = (float)e.pixel_sum[0][i] / div;
+        lights[((size_t)dst * nT + src) * 3 + i] = (float)e.light_sum[0][i] / div;
+      }
+    }
+    for (int src = 0; src < nT; src++) weights[(size_t)dst * nT + src] = (w_total != 0.0f) ? wrow[src] / w_total : 0.0f;
+  }
+}
+
+}  // namespace orc
+
+// ================================================================================================
+// C ABI for ctypes (tests, smoke, bench cpu_baseline only)
+// ================================================================================================
+using namespace orc;
+
+extern "C" {
+
+struct OrcParams {
+  int width, height, spp, max_depth;
+  float p_rr;
+  uint32_t seed_lo, seed_hi;
+  int group_samples;
+  int row_begin, row_end;
+};
+static Params to_params(const OrcParams* p) {
+  Params P;
+  P.width = p->width; P.height = p->height; P.spp = p->spp; P.max_depth = p->max_depth;
+  P.p_rr = p->p_rr; P.seed_lo = p->seed_lo; P.seed_hi = p->seed_hi; P.group_samples = p->group_samples;
+  P.row_begin = p->row_begin; P.row_end = p->row_end;
+  if (P.row_end <= 0 || P.row_end > P.height) P.row_end = P.height;
+  if (P.row_begin < 0) P.row_begin = 0;
+  return P;
+}
+
+static std::string g_err;
+const char* orc_last_error() { return g_err.c_str(); }
+
+void* orc_load_scene(const float* poss, const float* oris, const float* scls, const char* const* objs, const char* const* mtls,
+                     int n, const char* root) {
+  g_err.clear();
+  return load_scene(poss, oris, scls, objs, mtls, n, root, &g_err);
+}
+void orc_free_scene(void* h) { delete (Scene*)h; }
+int orc_num_triangles(void* h) { return ((Scene*)h)->nT; }
+int orc_num_emissives(void* h) { return (int)((Scene*)h)->emissives.size(); }
+
+// per-triangle dump for loader parity: verts[9], kd[3], ks[3], ke[3], ns, has_vn, normal[3], center[3], area
+void orc_get_triangle_table(void* h, float* verts, float* kd, float* ks, float* ke, float* ns, int* has_vn, float* normal,
+                            float* center, float* area, float* vnormals) {
+  Scene* sc = (Scene*)h;
+  for (int i = 0; i < sc->nT; i++) {
+    const Triangle& t = sc->tri(i);
+    for (int j = 0; j < 3; j++) {
+      verts[9 * i + 3 * j] = t.v[j].x; verts[9 * i + 3 * j + 1] = t.v[j].y; verts[9 * i + 3 * j + 2] = t.v[j].z;
+      if (vnormals) { vnormals[9 * i + 3 * j] = t.vn[j].x; vnormals[9 * i + 3 * j + 1] = t.vn[j].y; vnormals[9 * i + 3 * j + 2] = t.vn[j].z; }
+      kd[3 * i + j] = t.mat.kd[j]; ks[3 * i + j] = t.mat.ks[j]; ke[3 * i + j] = t.mat.ke[j];
+    }
+    ns[i] = t.mat.ns; has_vn[i] = t.has_vn ? 1 : 0;
+    normal[3 * i] = t.normal.x; normal[3 * i + 1] = t.normal.y; normal[3 * i + 2] = t.normal.z;
+    center[3 * i] = t.center.x; center[3 * i + 1] = t.center.y; center[3 * i + 2] = t.center.z;
+    area[i] = t.area;
+  }
+}
+// Scene::getMaterials / setMaterials, scene.h:145-162
+void orc_get_materials(void* h, float* m) {
+  Scene* sc = (Scene*)h;
+  for (int i = 0; i < sc->nT; i++) for (int j = 0; j < 3; j++) m[3 * i + j] = sc->tri(i).mat.kd[j];
+}
+void orc_set_materials(void* h, const float* m) {
+  Scene* sc = (Scene*)h;
+  for (int i = 0; i < sc->nT; i++) for (int j = 0; j < 3; j++) sc->tri(i).mat.kd[j] = m[3 * i + j];
+}
+void orc_get_camera(void* h, float* M16) { memcpy(M16, ((Scene*)h)->cam.M, 16 * sizeof(float)); }
+
+// closest hit for a ray batch: rays[n][6] = (p, d) -> tri id (-1 miss), t (inf miss)
+void orc_trace(void* h, const float* rays, int n, int* tri, float* t, int threads) {
+  Scene* sc = (Scene*)h;
+  parallel_rows(0, n, threads, [&](int i, int) {
+    Ray r{mk(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), mk(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])};
+    Hit hit = sc->closest_hit(r);
+    tri[i] = hit.tri;
+    t[i] = hit.t;
+  });
+}
+
+// forward render of rows [row_begin,row_end): img = float radiance means (rows*W*3, row-major from
+// row_begin), img8 optional tone-mapped u8; counters[3] = paths, extension rays, shadow rays
+void orc_render(void* h, const OrcParams* p, float* img, uint8_t* img8, uint64_t* counters, int threads) {
+  Scene* sc = (Scene*)h;
+  Params P = to_params(p);
+  if (threads < 1) threads = 1;
+  std::vector<Counters> cnt(threads);
+  parallel_rows(P.row_begin, P.row_end, threads, [&](int r, int tid) {
+    for (int c = 0; c < P.width; c++) {
+      float px[3];
+      render_pixel(*sc, P, r, c, px, &cnt[tid]);
+      size_t o = ((size_t)(r - P.row_begin) * P.width + c) * 3;
+      for (int i = 0; i < 3; i++) { if (img) img[o + i] = px[i]; if (img8) img8[o + i] = tonemap_u8(px[i]); }
+    }
+  });
+  if (counters) {
+    counters[0] = counters[1] = counters[2] = 0;
+    for (auto& c : cnt) { counters[0] += c.paths; counters[1] += c.ext_rays; counters[2] += c.shadow_rays; }
+  }
+}
+
+// one sample's radiance + its vertex trace (debugging / fine-grained parity)
+int orc_sample(void* h, const OrcParams* p, int r, int c, int s, float* L, int* tris, int max_tris) {
+  Scene* sc = (Scene*)h;
+  Params P = to_params(p);
+  Counters cnt;
+  std::vector<Vertex> tr;
+  render_sample(*sc, P, r, c, s, L, &cnt, &tr);
+  for (size_t i = 0; i < tr.size() && (int)i < max_tris; i++) tris[i] = tr[i].tri;
+  return (int)tr.size();
+}
+
+// createGraph, inv_path_trace.cu:195-208: target = u8 RGB image (height*width*3, full image);
+// raw (optional) = (nT+1)*nT*16 doubles [n,w,pix[2][3],light[2][3],fac[2]], rows dst=0..nT-1 then eye;
+// data = 7*(nT+1)*nT floats in the reference's output layout.
+void orc_create_graph(void* h, const OrcParams* p, const uint8_t* target, double* raw, float* data, uint64_t* counters, int threads) {
+  Scene* sc = (Scene*)h;
+  Params P = to_params(p);
+  const int nT = sc->nT;
+  if (threads < 1) threads = 1;
+  size_t nEdges = (size_t)(nT + 1) * nT;
+  std::vector<std::vector<Edge>> part(threads, std::vector<Edge>(nEdges));
+  std::vector<Counters> cnt(threads);
+  parallel_rows(P.row_begin, P.row_end, threads, [&](int r, int tid) {
+    for (int c = 0; c < P.width; c++) {
+      size_t o = ((size_t)r * P.width + c) * 3;
+      float pixel[3] = {(float)target[o] / 255.0f, (float)target[o + 1] / 255.0f, (float)target[o + 2] / 255.0f};  // inv_scene.h:74-77
+      for (int s = 0; s < P.spp; s++) graph_sample(*sc, P, r, c, s, pixel, part[tid], &cnt[tid]);
+    }
+  });
+  std::vector<Edge>& edges = part[0];
+  for (int t = 1; t < threads; t++) for (size_t e = 0; e < nEdges; e++) edges[e].merge(part[t][e]);
+  if (raw) {
+    for (size_t e = 0; e < nEdges; e++) {
+      double* o = raw + e * 16;
+      o[0] = (double)edges[e].n; o[1] = edges[e].w_sum;
+      for (int j = 0; j < 2; j++) for (int i = 0; i < 3; i++) { o[2 + j * 3 + i] = edges[e].pixel_sum[j][i]; o[8 + j * 3 + i] = edges[e].light_sum[j][i]; }
+      o[14] = edges[e].factors_sum[0]; o[15] = edges[e].factors_sum[1];
+    }
+  }
+  if (data) graph_compress(edges, nT, data);
+  if (counters) {
+    counters[0] = counters[1] = counters[2] = 0;
+    for (auto& c : cnt) { counters[0] += c.paths; counters[1] += c.ext_rays; counters[2] += c.shadow_rays; }
+  }
+}
+
+// NEW functionality (no reference counterpart; parity unpinned): loss + dLoss/dKd.
+//   image L = forward render (float canon); y = L/(1+L); y* = target/255;
+//   loss = sum over rows [row_begin,row_end) of (y-y*)^2 / (3*W*H)
+//   grad[t][c] = sum_pixels dloss/dL_c * (1/spp) * sum_samples dL_sample,c/dKd[t][c]
+// The estimator is polynomial in Kd and the sampling does not depend on Kd, so the gradient of the
+// estimator is exact (valid for Ks == 0 materials).  Accumulated in double here.
+void orc_render_grad(void* h, const OrcParams* p, const uint8_t* target, double* loss_out, double* grad, float* img, int threads) {
+  Scene* sc = (Scene*)h;
+  Params P = to_params(p);
+  const int nT = sc->nT;
+  if (threads < 1) threads = 1;
+  std::vector<std::vector<double>> gpart(threads, std::vector<double>((size_t)nT * 3, 0.0));
+  std::vector<double> lpart(threads, 0.0);
+  const double inv_n = 1.0 / (3.0 * (double)P.width * (double)P.height);
+  parallel_rows(P.row_begin, P.row_end, threads, [&](int r, int tid) {
+    Counters cnt;
+    std::vector<Vertex> tr;
+    for (int c = 0; c < P.width; c++) {
+      float px[3];
+      render_pixel(*sc, P, r, c, px, &cnt);
+      size_t o = ((size_t)r * P.width + c) * 3;
+      if (img) for (int i = 0; i < 3; i++) img[((size_t)(r - P.row_begin) * P.width + c) * 3 + i] = px[i];
+      double dLdpx[3];
+      for (int i = 0; i < 3; i++) {
+        double L = px[i], y = L / (1.0 + L), ys = (double)target[o + i] / 255.0;
+        lpart[tid] += (y - ys) * (y - ys) * inv_n;
+        dLdpx[i] = 2.0 * (y - ys) * inv_n / ((1.0 + L) * (1.0 + L)) / (double)P.spp;
+      }
+      for (int s = 0; s < P.spp; s++) {
+        float Ls[3];
+        tr.clear();
+        render_sample(*sc, P, r, c, s, Ls, &cnt, &tr);
+        // L = sum_k P_k (E + D'_k);  P_{k+1} = P_k Kd_k b_k;  D_k = Kd_k Ke_l g_k; on a miss D' = D_{k-1}.
+        int K = (int)tr.size();
+        for (int ch = 0; ch < 3; ch++) {
+          std::vector<double> Pk(K + 1, 0.0), C(K, 0.0);
+          double E = (K > 0 && tr[0].tri >= 0) ? sc->tri(tr[0].tri).mat.ke[ch] : 0.0;
+          Pk[0] = 1.0;
+          double Dprev = 0.0;
+          for (int k = 0; k < K; k++) {
+            double D = Dprev;
+            if (tr[k].tri >= 0) D = (tr[k].light >= 0) ? (double)sc->tri(tr[k].tri).mat.kd[ch] * ((double)sc->tri(tr[k].light).mat.ke[ch] * (double)tr[k].g) : 0.0;
+            C[k] = E + D;
+            Dprev = D;
+            Pk[k + 1] = (tr[k].tri >= 0 && tr[k].cont) ? Pk[k] * (double)sc->tri(tr[k].tri).mat.kd[ch] * (double)tr[k].b : 0.0;
+          }
+          // adjoint sweep: Pbar_k = C_k + Kd_k b_k Pbar_{k+1}
+          double Pbar_next = 0.0;
+          for (int k = K - 1; k >= 0; k--) {
+            int t = tr[k].tri;
+            if (t >= 0) {
+              double dC = (tr[k].light >= 0) ? (double)sc->tri(tr[k].light).mat.ke[ch] * (double)tr[k].g : 0.0;
+              double gk = Pk[k] * dC;
+              if (tr[k].cont) gk += Pk[k] * (double)tr[k].b * Pbar_next;
+              gpart[tid][(size_t)t * 3 + ch] += dLdpx[ch] * gk;
+              Pbar_next = C[k] + (tr[k].cont ? (double)sc->tri(t).mat.kd[ch] * (double)tr[k].b * Pbar_next : 0.0);
+            } else {
+              // miss: the stale D_{k-1} is re-added with P_k -> gradient flows to triangle t_{k-1}
+              if (k > 0 && tr[k - 1].tri >= 0 && tr[k - 1].light >= 0) {
+                double dC = (double)sc->tri(tr[k - 1].light).mat.ke[ch] * (double)tr[k - 1].g;
+                gpart[tid][(size_t)tr[k - 1].tri * 3 + ch] += dLdpx[ch] * Pk[k] * dC;
+              }
+              Pbar_next = C[k];
+            }
+          }
+        }
+      }
+    }
+  });
+  double loss = 0.0;
+  for (int t = 0; t < threads; t++) loss += lpart[t];
+  *loss_out = loss;
+  for (size_t i = 0; i < (size_t)nT * 3; i++) { double g = 0.0; for (int t = 0; t < threads; t++) g += gpart[t][i]; grad[i] = g; }
+}
+
+// BVH::build over caller-supplied primitives: boxes[n][6] (lo,hi), pos[n][3].  Returns node count;
+// nodes_out[max_nodes][9] = lo[3],hi[3],start,nPrims,rightOffset (ints bit-cast into floats are
+// avoided: the three ints go to nodes_int[max_nodes][3]).
+int orc_bvh_build(const float* boxes, const float* pos, int n, int leaf_size, float* nodes_box, int* nodes_int, int max_nodes, int* perm) {
+  std::vector<Box> b(n);
+  std::vector<V3> p(n);
+  for (int i = 0; i < n; i++) {
+    b[i].lo = mk(boxes[6 * i], boxes[6 * i + 1], boxes[6 * i + 2]);
+    b[i].hi = mk(boxes[6 * i + 3], boxes[6 * i + 4], boxes[6 * i + 5]);
+    p[i] = mk(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+  }
+  std::vector<FlatNode> nodes;
+  std::vector<int> pm;
+  bvh_build(b.data(), p.data(), n, leaf_size, &nodes, &pm);
+  for (size_t i = 0; i < nodes.size() && (int)i < max_nodes; i++) {
+    for (int k = 0; k < 3; k++) { nodes_box[6 * i + k] = nodes[i].lo[k]; nodes_box[6 * i + 3 + k] = nodes[i].hi[k]; }
+    nodes_int[3 * i] = nodes[i].start; nodes_int[3 * i + 1] = nodes[i].nPrims; nodes_int[3 * i + 2] = nodes[i].rightOffset;
+  }
+  for (int i = 0; i < n; i++) perm[i] = pm[i];
+  return (int)nodes.size();
+}
+
+// object-level primitives of a loaded scene exactly as the reference feeds bvh.h: box = {pos} U verts,
+// position = obj.pos (scene_basics.h:405-424)
+void orc_object_prims(void* h, float* boxes, float* pos) {
+  Scene* sc = (Scene*)h;
+  for (size_t o = 0; o < sc->objects.size(); o++) {
+    const Object& ob = sc->objects[o];
+    boxes[6 * o] = ob.bbox.lo.x; boxes[6 * o + 1] = ob.bbox.lo.y; boxes[6 * o + 2] = ob.bbox.lo.z;
+    boxes[6 * o + 3] = ob.bbox.hi.x; boxes[6 * o + 4] = ob.bbox.hi.y; boxes[6 * o + 5] = ob.bbox.hi.z;
+    pos[3 * o] = ob.pos.x; pos[3 * o + 1] = ob.pos.y; pos[3 * o + 2] = ob.pos.z;
+  }
+}
+int orc_num_objects(void* h) { return (int)((Scene*)h)->objects.size(); }
+
+void orc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
+void orc_uniforms(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t stream, float* u) {
+  Rng r; r.key[0] = seed_lo; r.key[1] = seed_hi; r.pixel = pixel; r.sample = sample;
+  r.draw(bounce, stream, u);
+}
+void orc_sincos2pi(float u, float* s, float* c) { sincos2pi(u, s, c); }
+void orc_sample_dir(const float* n, float u_phi, float u_theta, float* out) {
+  V3 nd;
+  sample_next_dir(mk(n[0], n[1], n[2]), false, 0.0f, u_phi, u_theta, &nd);
+  out[0] = nd.x; out[1] = nd.y; out[2] = nd.z;
+}
+int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"
