@@ -1,0 +1,128 @@
+/* ipt_b200.h -- C ABI of libipt_b200.so, the B200-native drop-in for the rendering hot path of
+ * bblinn2017/inverse_path_tracer.
+ *
+ * Part 1 is exactly what the reference's FFI for this path binds (ipt_cuda.py:7-8 loads
+ * ./build/libipt.so and ./build/libpt.so and calls these six symbols through ctypes).  Both file
+ * names are provided as symlinks to this one library, so a scene made through one name can be used
+ * and freed through the other (ipt_cuda.py:112,134 does exactly that).
+ *
+ * Part 2 adds runtime parameters, raw outputs, ray batches, the material adjoint and device-pointer
+ * entry points.  Every extension returns 0 on success and -1 on failure; the message is available
+ * from iptGetLastError().  No entry point ever calls exit() (the reference does on load errors,
+ * scene_basics.h:164,216-220).  Plain pointers and sizes only -- no torch types.
+ */
+#ifndef IPT_B200_H
+#define IPT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 1 -- the reference's six entry points
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces scene.h:177-193.  poss/oris/scls: n pointers to 3 floats (position, axis-angle vector,
+ * scale); obj_fs: n OBJ paths; mtl_fs: n MTL paths or inline "*Kd r g b*" strings.  All caller-owned
+ * and only read during the call.  Writes an opaque library-owned handle to *scenePtr and returns
+ * the triangle count (0 and a NULL handle on failure). */
+int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mtl_fs, int n, void** scenePtr);
+
+/* replaces scene.h:195-199 */
+void freeScene(void* scenePtr);
+
+/* replaces path_trace.cu:227-234: renders 500x500 at 100 spp (scene.h:8-10), Russian roulette .9,
+ * unbounded depth, Reinhard u8, and writes an 8-bit RGB PNG.  The seed is time(NULL) like the
+ * reference unless the environment variable IPT_SEED is set. */
+void createImage(void* scenePtr, char* img_file);
+
+/* replaces inv_path_trace.cu:195-208: reads the 500x500 target PNG, accumulates the light-transport
+ * edge statistics and writes 7*(nT+1)*nT floats [weights | pixels | lights] into caller memory. */
+void createGraph(void* scenePtr, char* imgFile, float* data);
+
+/* replace inv_path_trace.cu:210-214 and :216-221: nT*3 diffuse albedos in triangle order */
+void getMaterials(void* scenePtr, float* materials);
+void setMaterials(void* scenePtr, float* materials);
+
+/* ------------------------------------------------------------------------------------------------
+ * Part 2 -- extensions
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct IptRenderParams {
+  int width, height;      /* scene.h:8-9   (500, 500)  */
+  int spp;                /* scene.h:10    (100)       */
+  int max_depth;          /* <= 0: unbounded like the reference; else max radiance() calls per path */
+  float p_rr;             /* scene.h:11    (.9f)       */
+  uint32_t seed_lo, seed_hi;   /* Philox key */
+  int group_samples;      /* samples accumulated sequentially per partial sum (<= 0: spp) */
+  int row_begin, row_end; /* pixel-row shard [begin, end); row_end <= 0 means height */
+} IptRenderParams;
+
+const char* iptGetLastError(void);
+void iptDefaultParams(IptRenderParams* p);
+/* directory prepended to relative asset paths in loadScene ("" = current directory, the reference behaviour) */
+int iptSetAssetRoot(const char* root);
+/* CUDA device used by scenes loaded afterwards from this thread (default -1: current device).
+ * -2 loads host-only handles (loader tables, get/setMaterials); every compute call on them fails. */
+int iptSetDevice(int device);
+/* 0 = auto (brute force up to 128 triangles, BVH above), 1 = force brute force, 2 = force BVH */
+int iptSetTraversalMode(int mode);
+
+int iptSceneInfo(void* scene, int* n_triangles, int* n_emissives, int* n_objects, int* n_bvh_nodes, int* uses_bvh);
+/* loader tables (triangle order defines ids): verts[nT*9], kd/ks/ke[nT*3], ns[nT], has_vn[nT],
+ * normal/center[nT*3], area[nT]; any pointer may be NULL */
+int iptGetTriangleTable(void* scene, float* verts, float* kd, float* ks, float* ke, float* ns, int* has_vn,
+                        float* normal, float* center, float* area);
+int iptGetCamera(void* scene, float* m16);
+
+/* closest hit for n rays (p.xyz, d.xyz); tri = -1 and t = +inf on a miss.  Host buffers. */
+int iptTraceRays(void* scene, const float* rays, int n, int* tri, float* t);
+/* same on device memory, asynchronous on `stream` (a cudaStream_t) */
+int iptTraceRaysDevice(void* scene, const float* rays_dev, int n, int* tri_dev, float* t_dev, void* stream);
+
+/* forward render of the row shard.  img: rows*width*3 float radiance means (may be NULL);
+ * img8: rows*width*3 tone-mapped bytes (may be NULL); counters[3] = paths, extension rays,
+ * shadow rays (may be NULL).  Host buffers, synchronous. */
+int iptRender(void* scene, const IptRenderParams* p, float* img, unsigned char* img8, unsigned long long* counters);
+/* device buffers, asynchronous on `stream`; counters_dev is zeroed by the call */
+int iptRenderDevice(void* scene, const IptRenderParams* p, float* img_dev, unsigned char* img8_dev,
+                    unsigned long long* counters_dev, void* stream);
+int iptCreateImageEx(void* scene, const IptRenderParams* p, const char* png_path);
+
+/* createGraph with runtime parameters.  target: height*width*3 bytes (host).  raw (optional):
+ * (nT+1)*nT*16 doubles per edge [n, w_sum, pixel_sum[2][3], light_sum[2][3], factors_sum[2]],
+ * rows dst = 0..nT-1 then the eye row; data (optional): 7*(nT+1)*nT floats (reference layout). */
+int iptCreateGraphEx(void* scene, const IptRenderParams* p, const unsigned char* target, double* raw, float* data,
+                     unsigned long long* counters);
+/* raw edge sums of this shard only, left on the device (all-reduce them, then iptGraphCompress) */
+int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsigned char* target_dev, double* raw_dev, void* stream);
+/* DataWrapper::compress (inv_scene.h:87-115) on host arrays */
+int iptGraphCompress(const double* raw, int n_triangles, float* data);
+
+/* NEW (no reference counterpart): loss = sum over the shard of (L/(1+L) - target/255)^2 / (3*W*H) and
+ * its gradient with respect to every diffuse albedo, nT*3 doubles.  max_depth is clamped to 64. */
+int iptRenderGrad(void* scene, const IptRenderParams* p, const unsigned char* target, double* loss, double* grad, float* img);
+/* device buffers: lossgrad_dev[1 + nT*3] doubles (loss first), img_dev optional; asynchronous */
+int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned char* target_dev, double* lossgrad_dev,
+                        float* img_dev, void* stream);
+/* albedos from device memory (nT*3 floats), asynchronous on `stream` */
+int iptSetMaterialsDevice(void* scene, const float* kd_dev, void* stream);
+
+/* GPU BVH builder reproducing BVH::build (bvh.h:109-205) over n primitives: boxes[n*6] (lo, hi),
+ * pos[n*3] (split positions).  Outputs: node_boxes[max_nodes*6], node_ints[max_nodes*3] =
+ * (start, nPrims, rightOffset), perm[n] (primitive order).  Returns the node count or -1. */
+int iptBuildBVH(const float* boxes, const float* pos, int n, int leaf_size, float* node_boxes, int* node_ints,
+                int max_nodes, int* perm);
+
+int iptWritePNG(const char* path, const unsigned char* rgb, int width, int height);
+int iptReadPNG(const char* path, unsigned char* rgb, int capacity_bytes, int* width, int* height);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+unsigned long long iptKernelLaunchCount(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPT_B200_H */

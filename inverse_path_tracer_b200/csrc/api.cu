@@ -1,0 +1,723 @@
+// api.cu -- the C ABI of libipt_b200.so (declarations and reference citations: include/ipt_b200.h).
+//
+// A scene handle owns: the host description (for getMaterials / tables), the flat device arrays of
+// device_scene.h, one CUDA stream, and lazily grown scratch buffers.  No managed memory, no pointer
+// graph.  Handles are kept in a registry so freeScene()/setMaterials() through either library name
+// (libpt.so / libipt.so are the same file) validate what they are given.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/ipt_b200.h"
+#include "device_scene.h"
+#include "kernels.h"
+#include "scene_host.h"
+
+namespace ipt {
+
+static thread_local std::string g_error;
+static std::string g_asset_root;
+static thread_local int g_device = -1;
+static int g_traversal_mode = 0;
+static std::atomic<unsigned long long> g_launches(0);
+static std::mutex g_registry_mutex;
+static std::set<void*> g_registry;
+
+constexpr int kBruteForceMaxTris = 128;
+
+static int fail(const std::string& msg) {
+  g_error = msg;
+  return -1;
+}
+#define IPT_CUDA(call)                                                                                        \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e__));                 \
+  } while (0)
+
+struct Scratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+};
+
+struct SceneHandle {
+  HostScene host;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  float4* geom = nullptr;
+  float4* mat = nullptr;
+  float4* light = nullptr;
+  float4* vtx = nullptr;
+  float4* bvh_nodes = nullptr;
+  int* bvh_prims = nullptr;
+  int n_nodes = 0;
+  bool use_bvh = false;
+  bool host_only = false;   // loaded with iptSetDevice(-2): tables only, no device arrays
+  Scratch partial, counters, cnt_out, block_acc, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
+  std::mutex mutex;
+
+  DevScene dev() const {
+    DevScene d;
+    d.geom = geom; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_prims = bvh_prims;
+    d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.use_bvh = use_bvh ? 1 : 0;
+    memcpy(d.cam, host.cam, sizeof(d.cam));
+    return d;
+  }
+  void destroy() {
+    if (host_only) return;
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(geom); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_prims);
+    Scratch* all[] = {&partial, &counters, &cnt_out, &block_acc, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
+    for (Scratch* s : all) s->release();
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+static SceneHandle* checked(void* p) {
+  std::lock_guard<std::mutex> lk(g_registry_mutex);
+  if (!p || !g_registry.count(p)) { g_error = "invalid scene handle"; return nullptr; }
+  return (SceneHandle*)p;
+}
+// compute entry points: the scene must live on a GPU (there is no CPU fallback)
+static SceneHandle* checked_device(void* p) {
+  SceneHandle* h = checked(p);
+  if (h && h->host_only) { g_error = "scene was loaded host-only (iptSetDevice(-2)); compute needs a CUDA device"; return nullptr; }
+  return h;
+}
+
+static void pack_materials(const HostScene& hs, std::vector<float4>* mat) {
+  const size_t nT = hs.tris.size();
+  mat->resize(3 * nT);
+  for (size_t i = 0; i < nT; i++) {
+    const HostTriangle& t = hs.tris[i];
+    const bool any_ks = t.mat.ks[0] != 0.0f || t.mat.ks[1] != 0.0f || t.mat.ks[2] != 0.0f;
+    int flags = (t.has_vn ? TRI_HAS_VN : 0) | (any_ks ? TRI_ANY_KS : 0) | ((any_ks && t.mat.ns != 0.0f) ? TRI_SPECULAR : 0);   // path_trace.cu:132
+    float fbits;
+    memcpy(&fbits, &flags, 4);
+    (*mat)[3 * i + 0] = make_float4(t.mat.kd[0], t.mat.kd[1], t.mat.kd[2], t.mat.ns);
+    (*mat)[3 * i + 1] = make_float4(t.mat.ke[0], t.mat.ke[1], t.mat.ke[2], fbits);
+    (*mat)[3 * i + 2] = make_float4(t.mat.ks[0], t.mat.ks[1], t.mat.ks[2], t.area);
+  }
+}
+
+static int upload_scene(SceneHandle* h) {
+  const HostScene& hs = h->host;
+  const size_t nT = hs.tris.size(), nE = hs.emissives.size();
+  std::vector<float4> geom(4 * nT), mat, light(3 * std::max<size_t>(nE, 1)), vtx(5 * nT);
+  for (size_t i = 0; i < nT; i++) {
+    const HostTriangle& t = hs.tris[i];
+    geom[4 * i] = make_float4(t.n[0], t.n[1], t.n[2], t.plane_k);
+    for (int j = 0; j < 3; j++) geom[4 * i + 1 + j] = make_float4(t.edge[j][0], t.edge[j][1], t.edge[j][2], t.edge[j][3]);
+    vtx[5 * i + 0] = make_float4(t.v[0][0], t.v[0][1], t.v[0][2], t.vn[0][0]);
+    vtx[5 * i + 1] = make_float4(t.v[1][0], t.v[1][1], t.v[1][2], t.vn[0][1]);
+    vtx[5 * i + 2] = make_float4(t.v[2][0], t.v[2][1], t.v[2][2], t.vn[0][2]);
+    vtx[5 * i + 3] = make_float4(t.vn[1][0], t.vn[1][1], t.vn[1][2], t.area);
+    vtx[5 * i + 4] = make_float4(t.vn[2][0], t.vn[2][1], t.vn[2][2], 0.0f);
+  }
+  pack_materials(hs, &mat);
+  for (size_t k = 0; k < nE; k++) {
+    const HostTriangle& t = hs.tris[hs.emissives[k]];
+    int ti = t.idx;
+    float tb;
+    memcpy(&tb, &ti, 4);
+    light[3 * k + 0] = make_float4(t.v[0][0], t.v[0][1], t.v[0][2], hs.light_cdf[k]);
+    light[3 * k + 1] = make_float4(t.v[1][0], t.v[1][1], t.v[1][2], hs.light_pt[k]);
+    light[3 * k + 2] = make_float4(t.v[2][0], t.v[2][1], t.v[2][2], tb);
+  }
+  IPT_CUDA(cudaMalloc(&h->geom, std::max<size_t>(geom.size(), 1) * sizeof(float4)));
+  IPT_CUDA(cudaMalloc(&h->mat, std::max<size_t>(mat.size(), 1) * sizeof(float4)));
+  IPT_CUDA(cudaMalloc(&h->light, light.size() * sizeof(float4)));
+  IPT_CUDA(cudaMalloc(&h->vtx, std::max<size_t>(vtx.size(), 1) * sizeof(float4)));
+  if (nT) {
+    IPT_CUDA(cudaMemcpy(h->geom, geom.data(), geom.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    IPT_CUDA(cudaMemcpy(h->mat, mat.data(), mat.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    IPT_CUDA(cudaMemcpy(h->vtx, vtx.data(), vtx.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  }
+  IPT_CUDA(cudaMemcpy(h->light, light.data(), light.size() * sizeof(float4), cudaMemcpyHostToDevice));
+
+  h->use_bvh = (g_traversal_mode == 2) || (g_traversal_mode == 0 && (int)nT > kBruteForceMaxTris);
+  if (h->use_bvh && nT) {
+    // triangle-level tree: box = vertex bounds, split position = triangle center (the analogue of
+    // Object::getBBox / getPosition, scene_basics.h:417-424, with triangles as primitives)
+    std::vector<float> boxes(6 * nT), pos(3 * nT);
+    for (size_t i = 0; i < nT; i++) {
+      const HostTriangle& t = hs.tris[i];
+      for (int k = 0; k < 3; k++) {
+        boxes[6 * i + k] = fminf(fminf(t.v[0][k], t.v[1][k]), t.v[2][k]);
+        boxes[6 * i + 3 + k] = fmaxf(fmaxf(t.v[0][k], t.v[1][k]), t.v[2][k]);
+        pos[3 * i + k] = t.c[k];
+      }
+    }
+    std::vector<BvhNodeHost> nodes;
+    std::vector<int> perm;
+    std::string err;
+    if (!build_bvh(boxes.data(), pos.data(), (int)nT, 4, &nodes, &perm, h->device, &err)) return fail("BVH build failed: " + err);
+    std::vector<float4> packed(2 * nodes.size());
+    for (size_t i = 0; i < nodes.size(); i++) {
+      int ro = nodes[i].rightOffset;
+      int sp = (nodes[i].start << 3) | (nodes[i].nPrims & 7);
+      float a, b;
+      memcpy(&a, &ro, 4);
+      memcpy(&b, &sp, 4);
+      packed[2 * i] = make_float4(nodes[i].lo[0], nodes[i].lo[1], nodes[i].lo[2], a);
+      packed[2 * i + 1] = make_float4(nodes[i].hi[0], nodes[i].hi[1], nodes[i].hi[2], b);
+    }
+    h->n_nodes = (int)nodes.size();
+    IPT_CUDA(cudaMalloc(&h->bvh_nodes, packed.size() * sizeof(float4)));
+    IPT_CUDA(cudaMalloc(&h->bvh_prims, perm.size() * sizeof(int)));
+    IPT_CUDA(cudaMemcpy(h->bvh_nodes, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    IPT_CUDA(cudaMemcpy(h->bvh_prims, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+struct Plan {
+  DevRender rp;
+  int rows;
+};
+
+static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan) {
+  (void)h;
+  if (!p) return fail("null render params");
+  if (p->width <= 0 || p->height <= 0 || p->spp <= 0) return fail("width, height and spp must be positive");
+  if (!(p->p_rr > 0.0f)) return fail("p_rr must be positive");
+  int rb = p->row_begin < 0 ? 0 : p->row_begin;
+  int re = (p->row_end <= 0 || p->row_end > p->height) ? p->height : p->row_end;
+  if (rb >= re) return fail("empty row shard");
+  if ((long long)p->width * p->height > 0x7fffffffLL) return fail("image too large");
+  DevRender& rp = plan->rp;
+  rp.width = p->width; rp.height = p->height; rp.spp = p->spp; rp.max_depth = p->max_depth;
+  rp.p_rr = p->p_rr; rp.key0 = p->seed_lo; rp.key1 = p->seed_hi;
+  rp.group_samples = (p->group_samples <= 0 || p->group_samples > p->spp) ? p->spp : p->group_samples;
+  rp.groups = (p->spp + rp.group_samples - 1) / rp.group_samples;
+  rp.pix_begin = rb * p->width;
+  rp.n_pix = (re - rb) * p->width;
+  plan->rows = re - rb;
+  return 0;
+}
+
+static int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev,
+                          cudaStream_t st) {
+  const DevScene sc = h->dev();
+  const DevRender& rp = plan.rp;
+  IPT_CUDA(h->partial.reserve((size_t)rp.n_pix * rp.groups * 3 * sizeof(float)));
+  IPT_CUDA(h->counters.reserve(8 * sizeof(unsigned long long)));
+  unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
+  IPT_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
+  if (counters_dev) IPT_CUDA(cudaMemsetAsync(counters_dev, 0, 3 * sizeof(unsigned long long), st));
+  DevOut out;
+  memset(&out, 0, sizeof(out));
+  out.work_counter = ctr + 4;
+  out.counters = counters_dev ? counters_dev : ctr;
+  out.partial = (float*)h->partial.ptr;
+  const size_t smem = paths_smem_bytes(sc, 0);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, smem);
+  IPT_CUDA(launch_paths(MODE_RENDER_ID, sc, rp, out, grid, smem, st));
+  IPT_CUDA(launch_resolve(out.partial, rp.n_pix, rp.groups, img_dev, img8_dev, st));
+  g_launches += 2;
+  return 0;
+}
+
+static uint64_t legacy_seed() {
+  const char* s = getenv("IPT_SEED");
+  if (s && *s) return strtoull(s, nullptr, 10);
+  return (uint64_t)time(nullptr);   // path_trace.cu:206
+}
+
+}  // namespace ipt
+
+using namespace ipt;
+
+extern "C" {
+
+const char* iptGetLastError(void) { return g_error.c_str(); }
+
+void iptDefaultParams(IptRenderParams* p) {
+  if (!p) return;
+  p->width = 500; p->height = 500; p->spp = 100;   // scene.h:8-10
+  p->max_depth = 0;
+  p->p_rr = 0.9f;                                  // scene.h:11
+  p->seed_lo = 0; p->seed_hi = 0;
+  p->group_samples = 64;
+  p->row_begin = 0; p->row_end = 0;
+}
+
+int iptSetAssetRoot(const char* root) { g_asset_root = root ? root : ""; return 0; }
+int iptSetDevice(int device) { g_device = device; return 0; }
+int iptSetTraversalMode(int mode) {
+  if (mode < 0 || mode > 2) return fail("traversal mode must be 0, 1 or 2");
+  g_traversal_mode = mode;
+  return 0;
+}
+unsigned long long iptKernelLaunchCount(void) { return g_launches.load(); }
+
+int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mtl_fs, int n, void** scenePtr) {
+  if (scenePtr) *scenePtr = nullptr;
+  if (!scenePtr || n < 0 || (n > 0 && (!poss || !oris || !scls || !obj_fs || !mtl_fs))) { fail("loadScene: bad arguments"); return 0; }
+  SceneHandle* h = new SceneHandle();
+  std::string err;
+  if (!build_host_scene(poss, oris, scls, obj_fs, mtl_fs, n, g_asset_root, &h->host, &err)) {
+    fprintf(stderr, "ipt_b200: loadScene failed: %s\n", err.c_str());
+    fail(err);
+    delete h;
+    return 0;
+  }
+  int dev = g_device;
+  if (dev == -2) {   // host-only handle: loader tables / materials without touching CUDA
+    h->host_only = true;
+    std::lock_guard<std::mutex> lk(g_registry_mutex);
+    g_registry.insert(h);
+    *scenePtr = h;
+    return (int)h->host.tris.size();
+  }
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) {
+    fail("ipt_b200: no CUDA device available (this library has no CPU fallback)");
+    fprintf(stderr, "%s\n", g_error.c_str());
+    delete h;
+    return 0;
+  }
+  h->device = dev;
+  cudaError_t e = cudaSetDevice(dev);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) {
+    fail(std::string("ipt_b200: CUDA initialisation failed (no CPU fallback): ") + cudaGetErrorString(e));
+    fprintf(stderr, "%s\n", g_error.c_str());
+    delete h;
+    return 0;
+  }
+  if (upload_scene(h) != 0) {
+    fprintf(stderr, "ipt_b200: scene upload failed: %s\n", g_error.c_str());
+    h->destroy();
+    delete h;
+    return 0;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_registry_mutex);
+    g_registry.insert(h);
+  }
+  *scenePtr = h;
+  return (int)h->host.tris.size();
+}
+
+void freeScene(void* scenePtr) {
+  {
+    std::lock_guard<std::mutex> lk(g_registry_mutex);
+    if (!scenePtr || !g_registry.erase(scenePtr)) return;
+  }
+  SceneHandle* h = (SceneHandle*)scenePtr;
+  h->destroy();
+  delete h;
+}
+
+void getMaterials(void* scenePtr, float* materials) {
+  SceneHandle* h = checked(scenePtr);
+  if (!h || !materials) return;
+  std::lock_guard<std::mutex> lk(h->mutex);
+  for (size_t i = 0; i < h->host.tris.size(); i++)
+    for (int j = 0; j < 3; j++) materials[3 * i + j] = h->host.tris[i].mat.kd[j];
+}
+
+void setMaterials(void* scenePtr, float* materials) {
+  SceneHandle* h = checked(scenePtr);
+  if (!h || !materials) return;
+  std::lock_guard<std::mutex> lk(h->mutex);
+  for (size_t i = 0; i < h->host.tris.size(); i++)
+    for (int j = 0; j < 3; j++) h->host.tris[i].mat.kd[j] = materials[3 * i + j];
+  if (h->host_only) return;
+  std::vector<float4> mat;
+  pack_materials(h->host, &mat);
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  if (!mat.empty()) cudaMemcpy(h->mat, mat.data(), mat.size() * sizeof(float4), cudaMemcpyHostToDevice);
+}
+
+int iptSetMaterialsDevice(void* scene, const float* kd_dev, void* stream) {
+  SceneHandle* h = checked_device(scene);
+  if (!h || !kd_dev) return fail("iptSetMaterialsDevice: bad arguments");
+  IPT_CUDA(cudaSetDevice(h->device));
+  const int nT = (int)h->host.tris.size();
+  // Kd occupies xyz of every third float4: strided 2D copy, 12 bytes per row into a 48-byte pitch
+  IPT_CUDA(cudaMemcpy2DAsync(h->mat, 3 * sizeof(float4), kd_dev, 3 * sizeof(float), 3 * sizeof(float), nT, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+  return 0;
+}
+
+int iptSceneInfo(void* scene, int* n_triangles, int* n_emissives, int* n_objects, int* n_bvh_nodes, int* uses_bvh) {
+  SceneHandle* h = checked(scene);
+  if (!h) return -1;
+  if (n_triangles) *n_triangles = (int)h->host.tris.size();
+  if (n_emissives) *n_emissives = (int)h->host.emissives.size();
+  if (n_objects) *n_objects = (int)h->host.objects.size();
+  if (n_bvh_nodes) *n_bvh_nodes = h->n_nodes;
+  if (uses_bvh) *uses_bvh = h->use_bvh ? 1 : 0;
+  return 0;
+}
+
+int iptGetTriangleTable(void* scene, float* verts, float* kd, float* ks, float* ke, float* ns, int* has_vn, float* normal,
+                        float* center, float* area) {
+  SceneHandle* h = checked(scene);
+  if (!h) return -1;
+  for (size_t i = 0; i < h->host.tris.size(); i++) {
+    const HostTriangle& t = h->host.tris[i];
+    for (int j = 0; j < 3; j++) {
+      if (verts) for (int k = 0; k < 3; k++) verts[9 * i + 3 * j + k] = t.v[j][k];
+      if (kd) kd[3 * i + j] = t.mat.kd[j];
+      if (ks) ks[3 * i + j] = t.mat.ks[j];
+      if (ke) ke[3 * i + j] = t.mat.ke[j];
+      if (normal) normal[3 * i + j] = t.n[j];
+      if (center) center[3 * i + j] = t.c[j];
+    }
+    if (ns) ns[i] = t.mat.ns;
+    if (has_vn) has_vn[i] = t.has_vn ? 1 : 0;
+    if (area) area[i] = t.area;
+  }
+  return 0;
+}
+
+int iptGetCamera(void* scene, float* m16) {
+  SceneHandle* h = checked(scene);
+  if (!h || !m16) return -1;
+  memcpy(m16, h->host.cam, 16 * sizeof(float));
+  return 0;
+}
+
+int iptTraceRaysDevice(void* scene, const float* rays_dev, int n, int* tri_dev, float* t_dev, void* stream) {
+  SceneHandle* h = checked_device(scene);
+  if (!h) return -1;
+  if (n < 0 || (n > 0 && (!rays_dev || !tri_dev || !t_dev))) return fail("iptTraceRaysDevice: bad arguments");
+  if (n == 0) return 0;
+  IPT_CUDA(cudaSetDevice(h->device));
+  const int grid = std::min((n + 255) / 256, h->sm_count * 8);
+  IPT_CUDA(launch_trace_rays(h->dev(), rays_dev, n, tri_dev, t_dev, grid, (cudaStream_t)stream));
+  g_launches += 1;
+  return 0;
+}
+
+int iptTraceRays(void* scene, const float* rays, int n, int* tri, float* t) {
+  SceneHandle* h = checked_device(scene);
+  if (!h) return -1;
+  if (n < 0 || (n > 0 && (!rays || !tri || !t))) return fail("iptTraceRays: bad arguments");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lk(h->mutex);
+  IPT_CUDA(cudaSetDevice(h->device));
+  IPT_CUDA(h->rays.reserve((size_t)n * 6 * sizeof(float)));
+  IPT_CUDA(h->hits_tri.reserve((size_t)n * sizeof(int)));
+  IPT_CUDA(h->hits_t.reserve((size_t)n * sizeof(float)));
+  IPT_CUDA(cudaMemcpyAsync(h->rays.ptr, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (iptTraceRaysDevice(scene, (const float*)h->rays.ptr, n, (int*)h->hits_tri.ptr, (float*)h->hits_t.ptr, h->stream) != 0) return -1;
+  IPT_CUDA(cudaMemcpyAsync(tri, h->hits_tri.ptr, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  IPT_CUDA(cudaMemcpyAsync(t, h->hits_t.ptr, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  IPT_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int iptRenderDevice(void* scene, const IptRenderParams* p, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev,
+                    void* stream) {
+  SceneHandle* h = checked_device(scene);
+  if (!h) return -1;
+  Plan plan;
+  if (make_plan(h, p, &plan) != 0) return -1;
+  IPT_CUDA(cudaSetDevice(h->device));
+  return launch_forward(h, plan, img_dev, img8_dev, counters_dev, (cudaStream_t)stream);
+}
+
+int iptRender(void* scene, const IptRenderParams* p, float* img, unsigned char* img8, unsigned long long* counters) {
+  SceneHandle* h = checked_device(scene);
+  if (!h) return -1;
+  Plan plan;
+  if (make_plan(h, p, &plan) != 0) return -1;
+  std::lock_guard<std::mutex> lk(h->mutex);
+  IPT_CUDA(cudaSetDevice(h->device));
+  const size_t n3 = (size_t)plan.rp.n_pix * 3;
+  IPT_CUDA(h->img.reserve(n3 * sizeof(float)));
+  IPT_CUDA(h->img8.reserve(n3));
+  IPT_CUDA(h->cnt_out.reserve(4 * sizeof(unsigned long long)));
+  unsigned long long* cdev = (unsigned long long*)h->cnt_out.ptr;
+  if (launch_forward(h, plan, img ? (float*)h->img.ptr : nullptr, img8 ? (unsigned char*)h->img8.ptr : nullptr, cdev, h->stream) != 0) return -1;
+  if (img) IPT_CUDA(cudaMemcpyAsync(img, h->img.ptr, n3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (img8) IPT_CUDA(cudaMemcpyAsync(img8, h->img8.ptr, n3, cudaMemcpyDeviceToHost, h->stream));
+  if (counters) IPT_CUDA(cudaMemcpyAsync(counters, cdev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  IPT_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int iptCreateImageEx(void* scene, const IptRenderParams* p, const char* png_path) {
+  if (!p || !png_path) return fail("iptCreateImageEx: bad arguments");
+  IptRenderParams q = *p;
+  q.row_begin = 0;
+  q.row_end = 0;
+  std::vector<unsigned char> px((size_t)q.width * q.height * 3);
+  if (iptRender(scene, &q, nullptr, px.data(), nullptr) != 0) return -1;
+  std::string err;
+  if (!write_png_rgb8(png_path, px.data(), q.width, q.height, &err)) return fail(err);
+  return 0;
+}
+
+void createImage(void* scenePtr, char* img_file) {
+  IptRenderParams p;
+  iptDefaultParams(&p);
+  const uint64_t seed = legacy_seed();
+  p.seed_lo = (uint32_t)seed;
+  p.seed_hi = (uint32_t)(seed >> 32);
+  if (iptCreateImageEx(scenePtr, &p, img_file) != 0) fprintf(stderr, "ipt_b200: createImage failed: %s\n", g_error.c_str());
+}
+
+int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsigned char* target_dev, double* raw_dev, void* stream) {
+  SceneHandle* h = checked_device(scene);
+  if (!h) return -1;
+  if (!target_dev || !raw_dev) return fail("iptGraphAccumulateDevice: bad arguments");
+  Plan plan;
+  if (make_plan(h, p, &plan) != 0) return -1;
+  IPT_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevScene sc = h->dev();
+  const int nT = sc.nT;
+  const int n_edges = (nT + 1) * nT;
+  const int acc_floats = n_edges * kGraphAccPerEdge;
+  IPT_CUDA(cudaMemsetAsync(raw_dev, 0, (size_t)n_edges * 16 * sizeof(double), st));
+  if (nT == 0) return 0;
+  IPT_CUDA(h->counters.reserve(8 * sizeof(unsigned long long)));
+  unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
+  IPT_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
+  IPT_CUDA(h->acc.reserve((size_t)acc_floats * sizeof(double)));
+  IPT_CUDA(cudaMemsetAsync(h->acc.ptr, 0, (size_t)acc_floats * sizeof(double), st));
+  DevOut out;
+  memset(&out, 0, sizeof(out));
+  out.work_counter = ctr + 4;
+  out.counters = ctr;
+  out.target = target_dev;
+  out.acc_stride = acc_floats;
+  size_t smem = paths_smem_bytes(sc, acc_floats);
+  out.acc_in_smem = smem <= 160 * 1024 ? 1 : 0;
+  if (!out.acc_in_smem) smem = paths_smem_bytes(sc, 0);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAPH_ID, smem);
+  if (out.acc_in_smem) {
+    IPT_CUDA(h->block_acc.reserve((size_t)grid * acc_floats * sizeof(float)));
+    out.block_acc = (float*)h->block_acc.ptr;
+  } else {
+    out.global_acc = (double*)h->acc.ptr;
+  }
+  IPT_CUDA(launch_paths(MODE_GRAPH_ID, sc, plan.rp, out, grid, smem, st));
+  g_launches += 1;
+  if (out.acc_in_smem) {
+    IPT_CUDA(launch_reduce_blocks(out.block_acc, grid, acc_floats, (double*)h->acc.ptr, 8, kGraphAccPerEdge, st));
+    g_launches += 1;
+  }
+  IPT_CUDA(launch_graph_finalize((const double*)h->acc.ptr, h->mat, nT, n_edges, raw_dev, st));
+  g_launches += 1;
+  return 0;
+}
+
+// DataWrapper::compress + Edge::normalize (inv_scene.h:38-47, 87-115) on the raw sums
+int iptGraphCompress(const double* raw, int nT, float* data) {
+  if (!raw || !data || nT < 0) return fail("iptGraphCompress: bad arguments");
+  const size_t size = (size_t)(nT + 1) * nT;
+  float* weights = data;
+  float* pixels = data + size;
+  float* lights = data + 4 * size;
+  std::vector<float> row(nT);
+  for (int dst = 0; dst <= nT; dst++) {
+    float total = 0.0f;
+    for (int src = 0; src < nT; src++) {
+      const double* e = raw + ((size_t)dst * nT + src) * 16;
+      const float w = logf((float)e[1] + 1.0f);
+      const float fs = (float)e[14];
+      const float div = (fs != 0.0f) ? fs : 1.0f;
+      row[src] = w;
+      total += w;
+      for (int i = 0; i < 3; i++) {
+        pixels[((size_t)dst * nT + src) * 3 + i] = (float)e[2 + i] / div;
+        lights[((size_t)dst * nT + src) * 3 + i] = (float)e[8 + i] / div;
+      }
+    }
+    for (int src = 0; src < nT; src++) weights[(size_t)dst * nT + src] = (total != 0.0f) ? row[src] / total : 0.0f;
+  }
+  return 0;
+}
+
+int iptCreateGraphEx(void* scene, const IptRenderParams* p, const unsigned char* target, double* raw, float* data,
+                     unsigned long long* counters) {
+  SceneHandle* h = checked_device(scene);
+  if (!h) return -1;
+  if (!p || !target) return fail("iptCreateGraphEx: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mutex);
+  IPT_CUDA(cudaSetDevice(h->device));
+  const int nT = (int)h->host.tris.size();
+  const size_t n_edges = (size_t)(nT + 1) * nT;
+  const size_t tbytes = (size_t)p->width * p->height * 3;
+  IPT_CUDA(h->target.reserve(tbytes));
+  IPT_CUDA(h->raw.reserve(std::max<size_t>(n_edges, 1) * 16 * sizeof(double)));
+  IPT_CUDA(cudaMemcpyAsync(h->target.ptr, target, tbytes, cudaMemcpyHostToDevice, h->stream));
+  if (iptGraphAccumulateDevice(scene, p, (const unsigned char*)h->target.ptr, (double*)h->raw.ptr, h->stream) != 0) return -1;
+  std::vector<double> host_raw(n_edges * 16);
+  if (n_edges) IPT_CUDA(cudaMemcpyAsync(host_raw.data(), h->raw.ptr, n_edges * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (counters) IPT_CUDA(cudaMemcpyAsync(counters, h->counters.ptr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  IPT_CUDA(cudaStreamSynchronize(h->stream));
+  if (raw && n_edges) memcpy(raw, host_raw.data(), n_edges * 16 * sizeof(double));
+  if (data) return iptGraphCompress(host_raw.data(), nT, data);
+  return 0;
+}
+
+void createGraph(void* scenePtr, char* imgFile, float* data) {
+  SceneHandle* h = checked_device(scenePtr);
+  if (!h || !imgFile || !data) { fprintf(stderr, "ipt_b200: createGraph: bad arguments\n"); return; }
+  IptRenderParams p;
+  iptDefaultParams(&p);
+  const uint64_t seed = legacy_seed();
+  p.seed_lo = (uint32_t)seed;
+  p.seed_hi = (uint32_t)(seed >> 32);
+  std::vector<unsigned char> target;
+  int w = 0, hgt = 0;
+  std::string err;
+  if (!read_png_rgb8(imgFile, &target, &w, &hgt, &err)) { fail(err); fprintf(stderr, "ipt_b200: createGraph: %s\n", err.c_str()); return; }
+  if (w != p.width || hgt != p.height) {   // the reference silently assumes 500x500 (inv_scene.h:57)
+    fail("createGraph: target image must be 500x500");
+    fprintf(stderr, "ipt_b200: %s (got %dx%d)\n", g_error.c_str(), w, hgt);
+    return;
+  }
+  if (iptCreateGraphEx(scenePtr, &p, target.data(), nullptr, data, nullptr) != 0) fprintf(stderr, "ipt_b200: createGraph failed: %s\n", g_error.c_str());
+}
+
+int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned char* target_dev, double* lossgrad_dev, float* img_dev,
+                        void* stream) {
+  SceneHandle* h = checked_device(scene);
+  if (!h) return -1;
+  if (!p || !target_dev || !lossgrad_dev) return fail("iptRenderGradDevice: bad arguments");
+  IptRenderParams q = *p;
+  if (q.max_depth <= 0 || q.max_depth > kGradMaxDepth) q.max_depth = kGradMaxDepth;
+  Plan plan;
+  if (make_plan(h, &q, &plan) != 0) return -1;
+  IPT_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const DevScene sc = h->dev();
+  const DevRender& rp = plan.rp;
+  const int nT = sc.nT;
+  const size_t n3 = (size_t)rp.n_pix * 3;
+  float* img = img_dev;
+  if (!img) {
+    IPT_CUDA(h->img.reserve(n3 * sizeof(float)));
+    img = (float*)h->img.ptr;
+  }
+  if (launch_forward(h, plan, img, nullptr, nullptr, st) != 0) return -1;
+  IPT_CUDA(cudaMemsetAsync(lossgrad_dev, 0, (size_t)(1 + 3 * nT) * sizeof(double), st));
+  IPT_CUDA(h->dldpx.reserve(n3 * sizeof(float)));
+  const double inv_n = 1.0 / (3.0 * (double)rp.width * (double)rp.height);
+  IPT_CUDA(launch_loss_dldpx(img, target_dev, rp.pix_begin, rp.n_pix, inv_n, 1.0f / (float)rp.spp, (float*)h->dldpx.ptr, lossgrad_dev, st));
+  g_launches += 1;
+  if (nT == 0) return 0;
+  unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
+  IPT_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
+  DevOut out;
+  memset(&out, 0, sizeof(out));
+  out.work_counter = ctr + 4;
+  out.counters = ctr;
+  out.target = target_dev;
+  out.dldpx = (const float*)h->dldpx.ptr;
+  out.acc_stride = 3 * nT;
+  size_t smem = paths_smem_bytes(sc, 3 * nT);
+  out.acc_in_smem = smem <= 96 * 1024 ? 1 : 0;
+  if (!out.acc_in_smem) smem = paths_smem_bytes(sc, 0);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, smem);
+  if (out.acc_in_smem) {
+    IPT_CUDA(h->block_acc.reserve((size_t)grid * 3 * nT * sizeof(float)));
+    out.block_acc = (float*)h->block_acc.ptr;
+  } else {
+    out.global_acc = lossgrad_dev + 1;
+  }
+  IPT_CUDA(launch_paths(MODE_GRAD_ID, sc, rp, out, grid, smem, st));
+  g_launches += 1;
+  if (out.acc_in_smem) {
+    IPT_CUDA(launch_reduce_blocks(out.block_acc, grid, 3 * nT, lossgrad_dev + 1, 0, 0, st));
+    g_launches += 1;
+  }
+  return 0;
+}
+
+int iptRenderGrad(void* scene, const IptRenderParams* p, const unsigned char* target, double* loss, double* grad, float* img) {
+  SceneHandle* h = checked_device(scene);
+  if (!h) return -1;
+  if (!p || !target || !loss || !grad) return fail("iptRenderGrad: bad arguments");
+  std::lock_guard<std::mutex> lk(h->mutex);
+  IPT_CUDA(cudaSetDevice(h->device));
+  const int nT = (int)h->host.tris.size();
+  Plan plan;
+  if (make_plan(h, p, &plan) != 0) return -1;
+  const size_t tbytes = (size_t)p->width * p->height * 3;
+  const size_t n3 = (size_t)plan.rp.n_pix * 3;
+  IPT_CUDA(h->target.reserve(tbytes));
+  IPT_CUDA(h->lossgrad.reserve((size_t)(1 + 3 * nT) * sizeof(double)));
+  IPT_CUDA(h->img.reserve(n3 * sizeof(float)));
+  IPT_CUDA(cudaMemcpyAsync(h->target.ptr, target, tbytes, cudaMemcpyHostToDevice, h->stream));
+  if (iptRenderGradDevice(scene, p, (const unsigned char*)h->target.ptr, (double*)h->lossgrad.ptr, (float*)h->img.ptr, h->stream) != 0) return -1;
+  std::vector<double> lg(1 + 3 * (size_t)nT);
+  IPT_CUDA(cudaMemcpyAsync(lg.data(), h->lossgrad.ptr, lg.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (img) IPT_CUDA(cudaMemcpyAsync(img, h->img.ptr, n3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  IPT_CUDA(cudaStreamSynchronize(h->stream));
+  *loss = lg[0];
+  memcpy(grad, lg.data() + 1, 3 * (size_t)nT * sizeof(double));
+  return 0;
+}
+
+int iptBuildBVH(const float* boxes, const float* pos, int n, int leaf_size, float* node_boxes, int* node_ints, int max_nodes, int* perm) {
+  if (n < 0 || (n > 0 && (!boxes || !pos || !perm)) || !node_boxes || !node_ints) return fail("iptBuildBVH: bad arguments");
+  std::vector<BvhNodeHost> nodes;
+  std::vector<int> pm;
+  std::string err;
+  int dev = g_device;
+  if (dev < 0) cudaGetDevice(&dev);
+  if (!build_bvh(boxes, pos, n, leaf_size, &nodes, &pm, dev, &err)) return fail(err);
+  if ((int)nodes.size() > max_nodes) return fail("iptBuildBVH: max_nodes too small");
+  for (size_t i = 0; i < nodes.size(); i++) {
+    for (int k = 0; k < 3; k++) { node_boxes[6 * i + k] = nodes[i].lo[k]; node_boxes[6 * i + 3 + k] = nodes[i].hi[k]; }
+    node_ints[3 * i] = nodes[i].start; node_ints[3 * i + 1] = nodes[i].nPrims; node_ints[3 * i + 2] = nodes[i].rightOffset;
+  }
+  for (int i = 0; i < n; i++) perm[i] = pm[i];
+  return (int)nodes.size();
+}
+
+int iptWritePNG(const char* path, const unsigned char* rgb, int width, int height) {
+  std::string err;
+  if (!path || !rgb || width <= 0 || height <= 0) return fail("iptWritePNG: bad arguments");
+  if (!write_png_rgb8(path, rgb, width, height, &err)) return fail(err);
+  return 0;
+}
+
+int iptReadPNG(const char* path, unsigned char* rgb, int capacity_bytes, int* width, int* height) {
+  std::string err;
+  std::vector<unsigned char> px;
+  int w = 0, h = 0;
+  if (!path) return fail("iptReadPNG: bad arguments");
+  if (!read_png_rgb8(path, &px, &w, &h, &err)) return fail(err);
+  if (width) *width = w;
+  if (height) *height = h;
+  if (rgb) {
+    if ((size_t)capacity_bytes < px.size()) return fail("iptReadPNG: buffer too small");
+    memcpy(rgb, px.data(), px.size());
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// device_scene.h -- flat device-side scene layout and kernel launch descriptors.
+//
+// HBM layout.  All arrays are float4-vectorised so one triangle test is
+// four 16-byte loads and the whole small scene can be staged into shared memory with float4 copies.
+//   geom  [4*nT] : {n.xyz, k=dot(c,n)} {e0.xyz,e0.d} {e1.xyz,e1.d} {e2.xyz,e2.d}     64 B / triangle
+//   mat   [3*nT] : {Kd.rgb, Ns} {Ke.rgb, flags(bits)} {Ks.rgb, area}                 48 B / triangle
+//   light [3*nE] : {v0.xyz, cdf} {v1.xyz, p_t} {v2.xyz, tri index(bits)}             48 B / emissive
+//   vtx   [5*nT] : {v0.xyz, vn0.x} {v1.xyz, vn0.y} {v2.xyz, vn0.z} {vn1.xyz, area} {vn2.xyz, 0}
+//                  (only read for triangles that carry per-vertex normals: Triangle::getNormal)
+//   bvh nodes [2*nNodes] : {lo.xyz, start|rightOffset(bits)} {hi.xyz, nPrims(bits)}   32 B / node
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ipt {
+
+enum : int { TRI_HAS_VN = 1, TRI_SPECULAR = 2, TRI_ANY_KS = 4 };
+
+struct DevScene {
+  const float4* geom;
+  const float4* mat;
+  const float4* light;
+  const float4* vtx;
+  const float4* bvh_nodes;   // null in brute-force mode
+  const int* bvh_prims;      // triangle index per BVH slot
+  int nT, nE, nNodes;
+  int use_bvh;
+  float cam[16];
+};
+
+struct DevRender {
+  int width, height, spp, max_depth;
+  float p_rr;
+  uint32_t key0, key1;
+  int group_samples;    // samples per work item
+  int groups;           // work items per pixel
+  int pix_begin;        // first global pixel index of this shard
+  int n_pix;            // pixels in this shard
+};
+
+// counters[0..2] = paths, extension rays, shadow rays
+struct DevOut {
+  unsigned long long* work_counter;
+  unsigned long long* counters;
+  float* partial;            // [n_pix * groups * 3]  forward
+  const unsigned char* target;   // full-image RGB8 target (graph / grad)
+  const float* dldpx;        // [n_pix * 3] dLoss/dL_pixel / spp  (grad)
+  float* block_acc;          // [gridDim.x * acc_stride] per-block partial sums (graph / grad)
+  double* global_acc;        // direct global accumulation when the scene does not fit shared memory
+  int acc_stride;
+  int acc_in_smem;
+};
+
+constexpr int kGraphAccPerEdge = 10;   // W_i, Wpix_i[3], W_d, Wpix_d[3], n_i, n_d
+constexpr int kGradMaxDepth = 64;      // vertex stack depth of the adjoint pass
+
+}  // namespace ipt

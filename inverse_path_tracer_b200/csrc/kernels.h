@@ -1,0 +1,33 @@
+// kernels.h -- host-callable launchers implemented in kernels.cu / bvh_build.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "device_scene.h"
+
+namespace ipt {
+
+enum { MODE_RENDER_ID = 0, MODE_GRAPH_ID = 1, MODE_GRAD_ID = 2 };
+
+size_t paths_smem_bytes(const DevScene& sc, int acc_floats);
+int paths_blocks_per_sm(int mode, size_t smem);
+cudaError_t launch_paths(int mode, const DevScene& sc, const DevRender& rp, const DevOut& out, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_trace_rays(const DevScene& sc, const float* rays, int n, int* tri, float* t, int grid, cudaStream_t st);
+cudaError_t launch_resolve(const float* partial, int n_pix, int groups, float* img, unsigned char* img8, cudaStream_t st);
+cudaError_t launch_loss_dldpx(const float* img, const unsigned char* target, int pix_begin, int n_pix, double inv_n, float inv_spp,
+                              float* dldpx, double* loss, cudaStream_t st);
+cudaError_t launch_reduce_blocks(const float* block_acc, int n_blocks, int stride, double* out, int ints_from, int ints_per, cudaStream_t st);
+cudaError_t launch_graph_finalize(const double* acc, const float4* mat, int nT, int n_edges, double* raw, cudaStream_t st);
+
+// BVH::build (bvh.h:109-205) over generic primitives.  nodes: 9 values per node
+// (lo[3], hi[3] as floats; start, nPrims, rightOffset as ints); perm: primitive order.
+struct BvhNodeHost {
+  float lo[3], hi[3];
+  int start, nPrims, rightOffset;
+};
+bool build_bvh(const float* boxes, const float* pos, int n, int leaf_size, std::vector<BvhNodeHost>* nodes, std::vector<int>* perm,
+               int device, std::string* err);
+
+}  // namespace ipt

@@ -1,0 +1,218 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star): hit ids bit-exact, t within 1e-5 relative (we
+require bit-exact), images within RMSE tolerance (we require bit-exact for diffuse scenes because
+both sides implement the same FP32 canon), edge statistics / gradients within 1e-3 relative."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ASSETS, GOLDEN, random_rays, scene_objects
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(ipt, oracle, objects, **kw):
+    return ipt.Scene(objects, asset_root=ASSETS, **kw), oracle.OracleScene(objects, ASSETS)
+
+
+def _scene0(oracle):
+    return oracle.parse_scene_file(os.path.join(ASSETS, "scenes", "0.txt"))
+
+
+def adversarial_rays(osc):
+    """edge-grazing, shared-diagonal, coplanar ceiling/light seam (y = 2) and self-hit (t ~ EPSILON) rays"""
+    tab = osc.triangle_table()
+    v = tab["verts"].astype(np.float64)
+    rng = np.random.RandomState(11)
+    rays = []
+    eye = np.array([0.0, 0.0, 0.0])
+    for i in range(v.shape[0]):
+        for j in range(3):
+            a, b = v[i, j], v[i, (j + 1) % 3]
+            for s in (0.0, 0.25, 0.5, 1.0):   # points exactly on edges and vertices
+                q = a + s * (b - a)
+                for o in (eye, np.array([0.3, -0.4, 2.5]), rng.uniform(-1.5, 1.5, 3) + np.array([0, 0, 4.0])):
+                    d = q - o
+                    n = np.linalg.norm(d)
+                    if n > 1e-6:
+                        rays.append(np.concatenate([o, d / n]))
+        c = v[i].mean(0)
+        nrm = tab["normal"][i].astype(np.float64)
+        for eps in (0.0, 5e-3, 9.9e-3, 1.0e-2, 1.01e-2, 2e-2):   # origins on / just off the surface
+            for k in range(3):
+                d = rng.normal(size=3)
+                d /= np.linalg.norm(d)
+                rays.append(np.concatenate([c + eps * nrm, d]))
+                rays.append(np.concatenate([c - eps * nrm, d]))
+        # grazing directions (|n.d| around MIN_DOT = 1e-4)
+        t1 = v[i, 1] - v[i, 0]
+        t1 /= np.linalg.norm(t1)
+        for s in (0.0, 5e-5, 1e-4, 1.5e-4, -1e-4):
+            d = t1 + s * nrm
+            d /= np.linalg.norm(d)
+            rays.append(np.concatenate([c - 0.5 * t1 + 0.3 * nrm * (s != 0), d]))
+    return np.array(rays, np.float32)
+
+
+@pytest.mark.parametrize("scene,mode", [("scene0", 0), ("scene0", 2), ("cornell", 0), ("rotated_cubes", 0), ("rotated_cubes", 2),
+                                        ("cornell_sphere", 0), ("cornell_sphere", 1)])
+def test_closest_hit_bit_exact(ipt, oracle, scene, mode):
+    objects = _scene0(oracle) if scene == "scene0" else scene_objects(scene)
+    g, o = _pair(ipt, oracle, objects, traversal_mode=mode)
+    assert g.nT == o.nT and g.nE == o.nE
+    assert bool(g.uses_bvh) == (mode == 2 or (mode == 0 and g.nT > 128))
+    n = 2_000_000 if g.nT <= 64 else 200_000
+    rays = np.concatenate([random_rays(n, 5), adversarial_rays(o)])
+    tri_g, t_g = g.trace(rays)
+    tri_o, t_o = o.trace(rays)
+    assert np.array_equal(tri_g, tri_o), "hit ids differ at %s" % np.nonzero(tri_g != tri_o)[0][:10]
+    assert t_g.tobytes() == t_o.tobytes()
+    assert (tri_o >= 0).mean() > 0.5
+
+
+def test_trace_edge_cases(ipt, oracle):
+    g, o = _pair(ipt, oracle, scene_objects("cornell"))
+    tri, t = g.trace(np.zeros((0, 6), np.float32))
+    assert tri.shape == (0,)
+    rays = np.array([[0, 0, 0, 0, 0, -1], [0, 0, 0, 0, 0, 0], [0, 0, 4, 0, 1, 0], [np.nan, 0, 0, 0, 0, 1]], np.float32)
+    tri_g, t_g = g.trace(rays)
+    tri_o, t_o = o.trace(rays)
+    assert np.array_equal(tri_g, tri_o) and t_g.tobytes() == t_o.tobytes()
+    assert tri_g[0] == -1 and np.isinf(t_g[0])
+
+
+@pytest.mark.parametrize("scene,w,h,spp,depth,gs", [("scene0", 64, 48, 16, 0, 64), ("scene0", 40, 40, 70, 5, 32), ("cornell", 256, 256, 16, 5, 64),
+                                                    ("rotated_cubes", 48, 48, 8, 8, 3)])
+def test_forward_image_bit_exact(ipt, oracle, scene, w, h, spp, depth, gs):
+    objects = _scene0(oracle) if scene == "scene0" else scene_objects(scene)
+    g, o = _pair(ipt, oracle, objects)
+    pg = ipt.default_params(width=w, height=h, spp=spp, max_depth=depth, seed=1234, group_samples=gs)
+    po = oracle.make_params(w, h, spp, max_depth=depth, seed=1234, group_samples=gs)
+    img_g, img8_g, cnt_g = g.render(pg, want_u8=True)
+    img_o, img8_o, cnt_o = o.render(po, want_u8=True)
+    assert cnt_g == cnt_o
+    assert cnt_g["paths"] == w * h * spp
+    assert img_g.tobytes() == img_o.tobytes(), "max abs diff %g" % np.abs(img_g - img_o).max()
+    assert np.array_equal(img8_g, img8_o)
+
+
+def test_forward_vertex_normals_and_bvh(ipt, oracle):
+    """sphere.obj carries per-vertex normals (Triangle::getNormal path) and pushes the scene into BVH mode"""
+    objects = scene_objects("cornell_sphere")
+    g, o = _pair(ipt, oracle, objects)
+    assert g.uses_bvh
+    pg = ipt.default_params(width=48, height=48, spp=8, max_depth=6, seed=9)
+    po = oracle.make_params(48, 48, 8, max_depth=6, seed=9)
+    img_g, cnt_g = g.render(pg)
+    img_o, cnt_o = o.render(po)
+    assert cnt_g == cnt_o
+    assert img_g.tobytes() == img_o.tobytes()
+
+
+def test_row_sharding_and_determinism(ipt, oracle):
+    g = ipt.Scene(_scene0(oracle), asset_root=ASSETS)
+    p = ipt.default_params(width=96, height=80, spp=32, seed=3)
+    full, _ = g.render(p)
+    again, _ = g.render(p)
+    assert full.tobytes() == again.tobytes()
+    parts = []
+    for rb, re in ((0, 11), (11, 40), (40, 80)):
+        q = ipt.default_params(width=96, height=80, spp=32, seed=3, row_begin=rb, row_end=re)
+        parts.append(g.render(q)[0])
+    assert np.concatenate(parts, 0).tobytes() == full.tobytes()
+
+
+def test_golden_image_statistics(ipt, oracle):
+    """the reference's only known-answer output: preds/0_true.png (500x500, 100 spp)"""
+    G = json.load(open(os.path.join(GOLDEN, "golden_0_true.json")))
+    from PIL import Image
+    gold = np.asarray(Image.open(os.path.join(GOLDEN, "golden_0_true.png")).convert("RGB")).astype(np.float32)
+    g = ipt.Scene(_scene0(oracle), asset_root=ASSETS)
+    p = ipt.default_params(seed=2024)
+    _, img8, cnt = g.render(p, want_u8=True)
+    for k, (r0, r1, c0, c1) in G["regions"].items():
+        m = img8[r0:r1, c0:c1].reshape(-1, 3).mean(0)
+        assert np.abs(m - np.array(G["region_means_u8"][k])).max() < 1.5, (k, m, G["region_means_u8"][k])
+    rmse = np.sqrt((((img8.astype(np.float32) - gold) / 255.0) ** 2).mean())
+    assert rmse < 0.03, rmse   # two independent reference renders differ by 0.019
+
+
+def test_graph_parity(ipt, oracle):
+    objects = _scene0(oracle)
+    g, o = _pair(ipt, oracle, objects)
+    w, h, spp = 64, 64, 24
+    rng = np.random.RandomState(0)
+    target = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    pg = ipt.default_params(width=w, height=h, spp=spp, seed=77)
+    po = oracle.make_params(w, h, spp, seed=77)
+    raw_g, data_g, cnt_g = g.create_graph(pg, target)
+    raw_o, data_o, cnt_o = o.create_graph(po, target)
+    assert cnt_g == cnt_o
+    assert np.array_equal(raw_g[:, 0], raw_o[:, 0])                       # update counts are exact
+    assert raw_g[-g.nT:, 0].sum() == cnt_g["paths"]                        # eye row: one update per primary hit (closed box)
+    np.testing.assert_allclose(raw_g, raw_o, rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(data_g, data_o, rtol=1e-3, atol=1e-6)
+    size = (g.nT + 1) * g.nT
+    rows = data_g[:size].reshape(g.nT + 1, g.nT).sum(1)
+    assert np.all((np.abs(rows - 1) < 1e-4) | (rows == 0))
+    assert not np.isnan(data_g).any()
+
+
+def test_grad_parity_and_finite_differences(ipt, oracle):
+    objects = _scene0(oracle)
+    g, o = _pair(ipt, oracle, objects)
+    w, h, spp = 32, 32, 16
+    rng = np.random.RandomState(1)
+    target = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    kd = rng.uniform(0.2, 0.8, (g.nT, 3)).astype(np.float32)
+    g.set_materials(kd)
+    o.set_materials(kd)
+    pg = ipt.default_params(width=w, height=h, spp=spp, seed=5, max_depth=64)
+    po = oracle.make_params(w, h, spp, seed=5, max_depth=64)
+    loss_g, grad_g, img_g = g.render_grad(pg, target)
+    loss_o, grad_o, img_o = o.render_grad(po, target)
+    assert img_g.tobytes() == img_o.tobytes()
+    assert abs(loss_g - loss_o) <= 1e-9 * abs(loss_o)
+    scale = np.abs(grad_o).max()
+    assert np.abs(grad_g - grad_o).max() <= 1e-3 * scale
+    # central finite differences of the GPU loss itself on a few albedos
+    def loss_at(m):
+        g.set_materials(m)
+        return g.render_grad(pg, target)[0]
+    order = np.argsort(-np.abs(grad_o).ravel())[:4]
+    for flat in order:
+        t, c = divmod(int(flat), 3)
+        e = 1e-2
+        mp, mm = kd.copy(), kd.copy()
+        mp[t, c] += e
+        mm[t, c] -= e
+        fd = (loss_at(mp) - loss_at(mm)) / (2 * e)
+        assert abs(fd - grad_g[t, c]) <= 2e-3 * abs(fd) + 1e-9, (t, c, fd, grad_g[t, c])
+
+
+def test_legacy_abi_roundtrip(ipt, oracle, tmp_path, monkeypatch):
+    """the six reference entry points through the host-side mirror of ipt_cuda.py"""
+    from inverse_path_tracer_b200 import ipt_cuda
+    from PIL import Image
+    monkeypatch.setenv("IPT_SEED", "42")
+    monkeypatch.setattr(ipt_cuda, "ASSET_ROOT", ASSETS)
+    scenefile = os.path.join(ASSETS, "scenes", "0.txt")
+    n_t, ptr = ipt_cuda.load_scene(scenefile)
+    assert n_t == 30
+    L = ipt.lib()
+    png = str(tmp_path / "img.png")
+    L.createImage(ptr, png.encode())
+    im = np.asarray(Image.open(png))
+    assert im.shape == (500, 500, 3) and im.dtype == np.uint8
+    o = oracle.OracleScene.from_file(scenefile, ASSETS)
+    _, ref8, _ = o.render(oracle.make_params(500, 500, 100, seed=42, row_end=40), want_u8=True)
+    assert np.array_equal(im[:40], ref8)
+    L.freeScene(ptr)
+    w, pixel, light, labels = ipt_cuda.generate_data(scenefile, png)
+    assert w.shape == (31, 30) and pixel.shape == (31, 30, 3) and light.shape == (31, 30, 3) and labels.shape == (30, 3)
+    np.testing.assert_allclose(labels, o.get_materials(), rtol=0, atol=0)
+    out = str(tmp_path / "pred.png")
+    ipt_cuda.render_with_materials(scenefile, out, np.full((30, 3), 0.5, np.float32))
+    assert np.asarray(Image.open(out)).shape == (500, 500, 3)
