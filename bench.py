@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path on N B200s of one node, one JSON line on stdout (rank 0).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1      # the reference arm (CPU oracle)
+
+Workload (BASELINE.json configs[1]): CornellBox-Empty-CO forward path trace, 1024 x 1024, 1024 spp,
+max depth 8, Russian roulette .9, Philox seed = step index.  One step = one full render of the image.
+At N > 1 the pixel rows are sharded (contiguous blocks), the scene is replicated, and the row blocks are
+all-gathered over NCCL inside the timed region (strong scaling: the image is fixed).
+
+Numbers:
+  value        Mrays/s, whole job, device-resident (image left in HBM), CUDA events, max over ranks.
+               A ray is one closest-hit query (extension or shadow), counted by device counters.
+  e2e          same metric through the host-buffer C-ABI call (iptRender): every step uploads the
+               albedos (setMaterials) and reads the float image back to host memory.
+  roofline     FP32-pipe roofline of the dominant kernel k_paths<RENDER>: algorithmic FLOPs =
+               rays x 36 FLOP x nT triangles over the kernel's own CUDA-event time;
+               peak = SMs x 128 lanes x 2 x sm_max_mhz (MEASURED_PEAKS.json).  No tensor cores, and the
+               scene lives in shared memory, so neither "hbm" nor "tensor" bounds this kernel.
+  cpu_baseline the CPU oracle (oracle/, a port of the reference algorithm -- the reference has no CPU
+               renderer) on all host threads, on a bounded row band of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+ASSETS = os.path.join(ROOT, "tests", "golden", "assets")
+
+WORKLOAD = {"name": "CornellBox-Empty-CO forward path trace 1024x1024, 1024 spp, depth 8", "width": 1024, "height": 1024, "spp": 1024,
+            "max_depth": 8, "p_rr": 0.9, "group_samples": 64}
+CORNELL = [{"pos": [0, 0, 4], "ori": [0, 0, 0], "scl": [2, 2, 2], "obj": "./CornellBox/CornellBox-Empty-CO.obj",
+            "mtl": "./CornellBox/CornellBox-Empty-CO.mtl"}]
+FLOP_PER_TEST = 36   # denom 5 + numerator 6 + div 1 + point 6 + three edge planes 18
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm on the host cores (oracle port; the reference ships no CPU
+# renderer and cannot be compiled here -- SURVEY.md R4, 8c)
+# ----------------------------------------------------------------------------------------------------
+def cpu_band(height, rows):
+    b = max(0, height // 2 - rows // 2)
+    return b, min(height, b + rows)
+
+
+def run_cpu_sample(O, osc, seed, rows, threads):
+    w = WORKLOAD
+    rb, re = cpu_band(w["height"], rows)
+    P = O.make_params(w["width"], w["height"], w["spp"], max_depth=w["max_depth"], p_rr=w["p_rr"], seed=seed,
+                      group_samples=w["group_samples"], row_begin=rb, row_end=re)
+    t0 = time.perf_counter()
+    _, cnt = osc.render(P, threads=threads)
+    dt = time.perf_counter() - t0
+    return cnt, dt, (rb, re)
+
+
+def reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    osc = O.OracleScene(CORNELL, ASSETS)
+    threads = O.hardware_threads() or 1
+    rows = args.cpu_rows
+    for i in range(args.warmup):
+        run_cpu_sample(O, osc, 1000 + i, max(1, rows // 4), threads)
+    rays = paths = 0
+    total = 0.0
+    band = None
+    for i in range(args.steps):
+        cnt, dt, band = run_cpu_sample(O, osc, i, rows, threads)
+        rays += cnt["ext_rays"] + cnt["shadow_rays"]
+        paths += cnt["paths"]
+        total += dt
+    v = rays / total / 1e6
+    sample = "rows [%d,%d) of the %dx%d image at %d spp per step (%d paths/step), %d host threads" % (
+        band[0], band[1], WORKLOAD["width"], WORKLOAD["height"], WORKLOAD["spp"], paths // max(args.steps, 1), threads)
+    line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD["name"], "sampled": sample},
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "extra": {"mpaths_per_s": paths / total / 1e6}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------
+def b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import inverse_path_tracer_b200 as ipt
+    from inverse_path_tracer_b200 import native, parallel
+    from inverse_path_tracer_b200.torch_api import TorchScene, render_loss
+
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        raise SystemExit("bench.py --gpus %d must run under torchrun with WORLD_SIZE=%d (got %d)" % (args.gpus, args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    launches0 = native.lib().iptKernelLaunchCount()
+    w = dict(WORKLOAD)
+    if args.small:   # developer smoke: not a bench number
+        w.update(width=256, height=256, spp=64, name=w["name"] + " [SMALL DEV RUN 256x256x64 -- not a bench number]")
+    ts = TorchScene(CORNELL, asset_root=ASSETS, device=local)
+    nT = ts.nT
+    rb, re = parallel.shard_rows(w["height"], rank, world)
+    rows = re - rb
+
+    def params(seed, **kw):
+        base = dict(width=w["width"], height=w["height"], spp=w["spp"], max_depth=w["max_depth"], p_rr=w["p_rr"],
+                    group_samples=w["group_samples"], row_begin=rb, row_end=re, seed=seed)
+        base.update(kw)
+        return ipt.default_params(**base)
+
+    out = torch.empty((rows, w["width"], 3), dtype=torch.float32, device=dev)
+    counters = torch.zeros(3, dtype=torch.int64, device=dev)
+    total = torch.zeros(3, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(seed):
+        ts.render(params(seed), out=out, counters=counters)
+        total.add_(counters)
+        img = parallel.gather_rows(out, w["height"]) if world > 1 else out
+        flush.zero_()
+        return img
+
+    # ---- device-resident timing -----------------------------------------------------------------------
+    for i in range(args.warmup):
+        step(10_000 + i)
+    barrier()
+    total.zero_()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    kernel_ms = ts.scene.kernel_times_ms(args.steps)
+    cnt = [int(x) for x in total.tolist()]
+    paths = sum_over_ranks(cnt[0])
+    rays = sum_over_ranks(cnt[1] + cnt[2])
+    value = rays / (ms * 1e-3) / 1e6
+    # roofline of the dominant kernel on this rank (rank 0 reports its own)
+    local_rays = cnt[1] + cnt[2]
+    k_ms = float(np.mean(kernel_ms)) if len(kernel_ms) else float("nan")
+    peaks, peak_kind = measured_peaks()
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak_tflops = sm_count * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    achieved_tflops = (local_rays / max(args.steps, 1)) * FLOP_PER_TEST * nT / (k_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_k_paths_render.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- end to end through the host-buffer C ABI -------------------------------------------------------
+    host_img = np.empty((rows, w["width"], 3), np.float32)
+    kd = ts.scene.get_materials()
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def e2e_step(seed):
+        ts.scene.set_materials(kd)                                      # H2D: this step's inputs (albedos)
+        return ts.scene.render(params(seed), img=host_img)[1]           # D2H: the float image of this rank's rows
+
+    e2e_step(20_000)
+    barrier()
+    t0 = time.perf_counter()
+    e_rays = 0
+    for i in range(e2e_steps):
+        c = e2e_step(i)
+        e_rays += c["ext_rays"] + c["shadow_rays"]
+    torch.cuda.synchronize()
+    e_dt = max_over_ranks(time.perf_counter() - t0)
+    e_value = sum_over_ranks(e_rays) / e_dt / 1e6
+
+    # ---- headline point of BASELINE.json's metric: 512 x 512, 64 spp ------------------------------------
+    extra = {"mpaths_per_s": paths / (ms * 1e-3) / 1e6, "rays_per_path": rays / max(paths, 1),
+             "kernel_ms_mean": k_ms, "kernel_share_of_step": k_ms * args.steps / max(ms, 1e-9)}
+    if not args.no_extras:
+        hb, he = parallel.shard_rows(512, rank, world)
+        hp = lambda s: ipt.default_params(width=512, height=512, spp=64, max_depth=0, seed=s, row_begin=hb, row_end=he)
+        hout = torch.empty((he - hb, 512, 3), dtype=torch.float32, device=dev)
+        for i in range(3):
+            ts.render(hp(100 + i), out=hout, counters=counters)
+        barrier()
+        total.zero_()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        h0.record()
+        for i in range(reps):
+            ts.render(hp(i), out=hout, counters=counters)
+            total.add_(counters)
+            if world > 1:
+                parallel.gather_rows(hout, 512)
+            flush.zero_()
+        h1.record()
+        barrier()
+        hms = max_over_ranks(h0.elapsed_time(h1))
+        hc = [int(x) for x in total.tolist()]
+        extra["cornell_512x512_64spp_unbounded"] = {"mrays_per_s": sum_over_ranks(hc[1] + hc[2]) / (hms * 1e-3) / 1e6,
+                                                     "mpaths_per_s": sum_over_ranks(hc[0]) / (hms * 1e-3) / 1e6, "ms_per_frame": hms / reps}
+        # ---- inverse iterations/s (BASELINE config 3): scenes/0.txt, 500x500, 64 spp/iter, Adam on 30x3 albedos
+        from inverse_path_tracer_b200.ipt_cuda import parse_scene_file
+        objs = parse_scene_file(os.path.join(ASSETS, "scenes", "0.txt"))
+        inv = TorchScene(objs, asset_root=ASSETS, device=local)
+        from PIL import Image
+        target = torch.from_numpy(np.asarray(Image.open(os.path.join(ROOT, "tests", "golden", "golden_0_true.png")).convert("RGB")).copy()).to(dev)
+        ib, ie = parallel.shard_rows(500, rank, world)
+        kd_param = torch.full((inv.nT, 3), 0.5, device=dev, requires_grad=True)
+        opt = torch.optim.Adam([kd_param], lr=0.02)
+
+        def inv_iter(it):
+            opt.zero_grad(set_to_none=True)
+            p = ipt.default_params(width=500, height=500, spp=64, max_depth=0, seed=it, row_begin=ib, row_end=ie)
+            loss = render_loss(kd_param, inv, p, target)
+            loss.backward()
+            opt.step()
+            with torch.no_grad():
+                kd_param.clamp_(1e-3, 1.0)
+            return loss
+
+        for it in range(3):
+            inv_iter(1000 + it)
+        barrier()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 20
+        i0.record()
+        for it in range(iters):
+            last = inv_iter(it)
+        i1.record()
+        barrier()
+        ims = max_over_ranks(i0.elapsed_time(i1))
+        extra["inverse_scene0_500x500_64spp"] = {"iters_per_s": iters / (ims * 1e-3), "ms_per_iter": ims / iters, "loss_after": float(last)}
+        inv.close()
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        osc = O.OracleScene(CORNELL, ASSETS)
+        threads = O.hardware_threads() or 1
+        ccnt, cdt, band = run_cpu_sample(O, osc, 0, args.cpu_rows, threads)
+        cpu = {"value": (ccnt["ext_rays"] + ccnt["shadow_rays"]) / cdt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
+               "sample": "rows [%d,%d) of the %dx%d image at %d spp (%d paths, %.1f s), CPU oracle on %d host threads" % (
+                   band[0], band[1], WORKLOAD["width"], WORKLOAD["height"], WORKLOAD["spp"], ccnt["paths"], cdt, threads)}
+
+    launches = native.lib().iptKernelLaunchCount() - launches0
+    if rank == 0:
+        line = {"metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["name"], "scene": "CornellBox-Empty-CO (18 triangles, 2 emissive), scene replicated",
+                           "sharding": "contiguous pixel-row blocks, all-gather of the float image" if world > 1 else "single GPU",
+                           "rng": "Philox4x32-10 keyed (pixel, sample, bounce), seed = step index",
+                           "l2": "flushed between iterations by a 256 MiB device write (inside the timed region)"},
+                "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                             "frac": achieved_tflops / peak_tflops, "traffic": traffic,
+                             "peak_source": "%s: %d SMs x 128 lanes x 2 x sm_max_mhz %.0f" % (peak_kind, sm_count, peaks["sm_max_mhz"]),
+                             "algorithmic": "%d FLOP per ray-triangle test x %d triangles per ray" % (FLOP_PER_TEST, nT)},
+                "cpu_baseline": cpu,
+                "e2e": {"value": e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(nT * 3 * 4),
+                        "d2h_bytes_per_step": int(rows * w["width"] * 3 * 4 + 24), "steps": e2e_steps},
+                "gpu_launches": int(launches), "clocks": clocks, "extra": extra}
+        print(json.dumps(line), flush=True)
+    ts.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-rows", type=int, default=12, help="rows of the 1024-wide image rendered per CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--small", action="store_true", help="developer smoke run (not a bench number)")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200" and not args.small:
+        args.warmup = 3   # timing rule: at least three warm-up steps
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+    rank, world, _ = dist_env()
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torchrun on this node
+        port = 29500 + (os.getpid() % 2000)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -119,6 +119,14 @@ int iptBuildBVH(const float* boxes, const float* pos, int n, int leaf_size, floa
 int iptWritePNG(const char* path, const unsigned char* rgb, int width, int height);
 int iptReadPNG(const char* path, unsigned char* rgb, int capacity_bytes, int* width, int* height);
 
+/* device times (ms) of the most recent persistent path-kernel launches on this scene, newest first
+ * (CUDA events recorded on the launching stream around each k_paths launch; ring of 64).  Blocks until
+ * those launches have finished.  Returns how many were written, or -1. */
+int iptPathKernelTimes(void* scene, float* ms, int max_count);
+/* counters (paths, extension rays, shadow rays) of the last launch that used the scene's internal
+ * counter block (graph / grad passes, or render calls given no counter buffer); synchronous */
+int iptLastCounters(void* scene, unsigned long long* counters);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 unsigned long long iptKernelLaunchCount(void);
 

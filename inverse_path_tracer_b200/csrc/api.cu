@@ -73,7 +73,12 @@ struct SceneHandle {
   int* bvh_prims = nullptr;
   int n_nodes = 0;
   bool use_bvh = false;
-  bool host_only = false;   // loaded with iptSetDevice(-2): tables only, no device arrays
+  bool host_only = false;
+  // ring of CUDA event pairs bracketing the last kEventRing k_paths launches (roofline timing without
+  // synchronising inside a timed loop)
+  static constexpr int kEventRing = 64;
+  cudaEvent_t ev_start[kEventRing] = {}, ev_stop[kEventRing] = {};
+  unsigned long long ev_count = 0;   // loaded with iptSetDevice(-2): tables only, no device arrays
   Scratch partial, counters, cnt_out, block_acc, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
   std::mutex mutex;
 
@@ -92,6 +97,7 @@ struct SceneHandle {
     Scratch* all[] = {&partial, &counters, &cnt_out, &block_acc, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
     for (Scratch* s : all) s->release();
     if (stream) cudaStreamDestroy(stream);
+    for (int i = 0; i < kEventRing; i++) { if (ev_start[i]) cudaEventDestroy(ev_start[i]); if (ev_stop[i]) cudaEventDestroy(ev_stop[i]); }
   }
 };
 
@@ -181,8 +187,20 @@ static int upload_scene(SceneHandle* h) {
       float a, b;
       memcpy(&a, &ro, 4);
       memcpy(&b, &sp, 4);
-      packed[2 * i] = make_float4(nodes[i].lo[0], nodes[i].lo[1], nodes[i].lo[2], a);
-      packed[2 * i + 1] = make_float4(nodes[i].hi[0], nodes[i].hi[1], nodes[i].hi[2], b);
+      // The traversal copy of each box is padded.  The reference's triangle test accepts a hit whose
+      // ROUNDED hit point passes the edge planes, i.e. it tolerates a few ulps of the coordinate
+      // magnitude; a box that is exact in real arithmetic can therefore exclude a hit the brute-force
+      // loop accepts (seen with near axis-parallel rays through a vertex).  pad = 1e-5 * (1 + |coord|)
+      // is > 40x that tolerance.  iptBuildBVH (layout parity) returns the unpadded boxes.
+      float lo[3], hi[3];
+      for (int k = 0; k < 3; k++) {
+        const float m = fmaxf(fabsf(nodes[i].lo[k]), fabsf(nodes[i].hi[k]));
+        const float pad = 1e-5f * (1.0f + m);
+        lo[k] = nodes[i].lo[k] - pad;
+        hi[k] = nodes[i].hi[k] + pad;
+      }
+      packed[2 * i] = make_float4(lo[0], lo[1], lo[2], a);
+      packed[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], b);
     }
     h->n_nodes = (int)nodes.size();
     IPT_CUDA(cudaMalloc(&h->bvh_nodes, packed.size() * sizeof(float4)));
@@ -234,7 +252,13 @@ static int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsi
   out.partial = (float*)h->partial.ptr;
   const size_t smem = paths_smem_bytes(sc, 0);
   const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, smem);
-  IPT_CUDA(launch_paths(MODE_RENDER_ID, sc, rp, out, grid, smem, st));
+  {
+    const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
+    IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
+    IPT_CUDA(launch_paths(MODE_RENDER_ID, sc, rp, out, grid, smem, st));
+    IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
+    h->ev_count++;
+  }
   IPT_CUDA(launch_resolve(out.partial, rp.n_pix, rp.groups, img_dev, img8_dev, st));
   g_launches += 2;
   return 0;
@@ -302,6 +326,10 @@ int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mt
   cudaError_t e = cudaSetDevice(dev);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  for (int i = 0; i < SceneHandle::kEventRing && e == cudaSuccess; i++) {
+    e = cudaEventCreate(&h->ev_start[i]);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev_stop[i]);
+  }
   if (e != cudaSuccess) {
     fail(std::string("ipt_b200: CUDA initialisation failed (no CPU fallback): ") + cudaGetErrorString(e));
     fprintf(stderr, "%s\n", g_error.c_str());
@@ -520,7 +548,13 @@ int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsign
   } else {
     out.global_acc = (double*)h->acc.ptr;
   }
-  IPT_CUDA(launch_paths(MODE_GRAPH_ID, sc, plan.rp, out, grid, smem, st));
+  {
+    const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
+    IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
+    IPT_CUDA(launch_paths(MODE_GRAPH_ID, sc, plan.rp, out, grid, smem, st));
+    IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
+    h->ev_count++;
+  }
   g_launches += 1;
   if (out.acc_in_smem) {
     IPT_CUDA(launch_reduce_blocks(out.block_acc, grid, acc_floats, (double*)h->acc.ptr, 8, kGraphAccPerEdge, st));
@@ -647,7 +681,13 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
   } else {
     out.global_acc = lossgrad_dev + 1;
   }
-  IPT_CUDA(launch_paths(MODE_GRAD_ID, sc, rp, out, grid, smem, st));
+  {
+    const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
+    IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
+    IPT_CUDA(launch_paths(MODE_GRAD_ID, sc, rp, out, grid, smem, st));
+    IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
+    h->ev_count++;
+  }
   g_launches += 1;
   if (out.acc_in_smem) {
     IPT_CUDA(launch_reduce_blocks(out.block_acc, grid, 3 * nT, lossgrad_dev + 1, 0, 0, st));
@@ -678,6 +718,29 @@ int iptRenderGrad(void* scene, const IptRenderParams* p, const unsigned char* ta
   IPT_CUDA(cudaStreamSynchronize(h->stream));
   *loss = lg[0];
   memcpy(grad, lg.data() + 1, 3 * (size_t)nT * sizeof(double));
+  return 0;
+}
+
+int iptPathKernelTimes(void* scene, float* ms, int max_count) {
+  SceneHandle* h = checked_device(scene);
+  if (!h || !ms || max_count < 0) return -1;
+  IPT_CUDA(cudaSetDevice(h->device));
+  const unsigned long long have = h->ev_count < (unsigned long long)SceneHandle::kEventRing ? h->ev_count : SceneHandle::kEventRing;
+  const int n = (int)((unsigned long long)max_count < have ? max_count : have);
+  for (int i = 0; i < n; i++) {   // ms[0] = most recent launch
+    const int slot = (int)((h->ev_count - 1 - i) % SceneHandle::kEventRing);
+    IPT_CUDA(cudaEventSynchronize(h->ev_stop[slot]));
+    IPT_CUDA(cudaEventElapsedTime(&ms[i], h->ev_start[slot], h->ev_stop[slot]));
+  }
+  return n;
+}
+
+int iptLastCounters(void* scene, unsigned long long* counters) {
+  SceneHandle* h = checked_device(scene);
+  if (!h || !counters) return -1;
+  if (!h->counters.ptr) return fail("no path kernel has been launched on this scene yet");
+  IPT_CUDA(cudaSetDevice(h->device));
+  IPT_CUDA(cudaMemcpy(counters, h->counters.ptr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -31,7 +31,7 @@ EXPORTS = ["loadScene", "freeScene", "createImage", "createGraph", "getMaterials
            "iptSceneInfo", "iptGetTriangleTable", "iptGetCamera", "iptTraceRays", "iptTraceRaysDevice",
            "iptRender", "iptRenderDevice", "iptCreateImageEx", "iptCreateGraphEx", "iptGraphAccumulateDevice",
            "iptGraphCompress", "iptRenderGrad", "iptRenderGradDevice", "iptSetMaterialsDevice", "iptBuildBVH",
-           "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount"]
+           "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters"]
 
 
 def lib():
@@ -68,6 +68,8 @@ def lib():
         L.iptWritePNG.argtypes = [C.c_char_p, vp, C.c_int, C.c_int]
         L.iptReadPNG.argtypes = [C.c_char_p, vp, C.c_int, vp, vp]
         L.iptSetAssetRoot.argtypes = [C.c_char_p]
+        L.iptPathKernelTimes.argtypes = [vp, vp, C.c_int]
+        L.iptLastCounters.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -226,6 +228,19 @@ class Scene:
         cnt = np.zeros(3, np.uint64)
         _check(lib().iptCreateGraphEx(self.h, C.byref(p), _ptr(target), _ptr(raw), _ptr(data), _ptr(cnt)), "iptCreateGraphEx")
         return raw, data, {"paths": int(cnt[0]), "ext_rays": int(cnt[1]), "shadow_rays": int(cnt[2])}
+
+    def kernel_times_ms(self, count=1):
+        """device times of the most recent path-kernel launches, newest first"""
+        ms = np.zeros(count, np.float32)
+        k = lib().iptPathKernelTimes(self.h, _ptr(ms), count)
+        if k < 0:
+            raise RuntimeError("iptPathKernelTimes failed: " + last_error())
+        return ms[:k]
+
+    def last_counters(self):
+        cnt = np.zeros(3, np.uint64)
+        _check(lib().iptLastCounters(self.h, _ptr(cnt)), "iptLastCounters")
+        return {"paths": int(cnt[0]), "ext_rays": int(cnt[1]), "shadow_rays": int(cnt[2])}
 
     def render_grad(self, p, target_u8):
         target = np.ascontiguousarray(target_u8, np.uint8)
