@@ -66,6 +66,11 @@ struct SceneHandle {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   float4* geom = nullptr;
+  float4* planes = nullptr;
+  int2* grange = nullptr;
+  float4* slot_edges = nullptr;
+  int* slot_tri = nullptr;
+  int n_groups = 0;
   float4* mat = nullptr;
   float4* light = nullptr;
   float4* vtx = nullptr;
@@ -84,7 +89,7 @@ struct SceneHandle {
 
   DevScene dev() const {
     DevScene d;
-    d.geom = geom; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_prims = bvh_prims;
+    d.geom = geom; d.planes = planes; d.grange = grange; d.slot_edges = slot_edges; d.slot_tri = slot_tri; d.nGroups = n_groups; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_prims = bvh_prims;
     d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.use_bvh = use_bvh ? 1 : 0;
     memcpy(d.cam, host.cam, sizeof(d.cam));
     return d;
@@ -93,7 +98,7 @@ struct SceneHandle {
     if (host_only) return;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    cudaFree(geom); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_prims);
+    cudaFree(geom); cudaFree(planes); cudaFree(grange); cudaFree(slot_edges); cudaFree(slot_tri); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_prims);
     Scratch* all[] = {&partial, &counters, &cnt_out, &block_acc, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
     for (Scratch* s : all) s->release();
     if (stream) cudaStreamDestroy(stream);
@@ -115,16 +120,52 @@ static SceneHandle* checked_device(void* p) {
 
 static void pack_materials(const HostScene& hs, std::vector<float4>* mat) {
   const size_t nT = hs.tris.size();
-  mat->resize(3 * nT);
+  mat->resize(kMatStride * nT);
   for (size_t i = 0; i < nT; i++) {
     const HostTriangle& t = hs.tris[i];
     const bool any_ks = t.mat.ks[0] != 0.0f || t.mat.ks[1] != 0.0f || t.mat.ks[2] != 0.0f;
     int flags = (t.has_vn ? TRI_HAS_VN : 0) | (any_ks ? TRI_ANY_KS : 0) | ((any_ks && t.mat.ns != 0.0f) ? TRI_SPECULAR : 0);   // path_trace.cu:132
     float fbits;
     memcpy(&fbits, &flags, 4);
-    (*mat)[3 * i + 0] = make_float4(t.mat.kd[0], t.mat.kd[1], t.mat.kd[2], t.mat.ns);
-    (*mat)[3 * i + 1] = make_float4(t.mat.ke[0], t.mat.ke[1], t.mat.ke[2], fbits);
-    (*mat)[3 * i + 2] = make_float4(t.mat.ks[0], t.mat.ks[1], t.mat.ks[2], t.area);
+    const float pi = 3.14159274f;   // (float)M_PI; Kd / pi is the indirect BSDF (path_trace.cu:15-17), divided once here
+    (*mat)[kMatStride * i + 0] = make_float4(t.mat.kd[0], t.mat.kd[1], t.mat.kd[2], t.mat.ns);
+    (*mat)[kMatStride * i + 1] = make_float4(t.mat.ke[0], t.mat.ke[1], t.mat.ke[2], fbits);
+    (*mat)[kMatStride * i + 2] = make_float4(t.mat.kd[0] / pi, t.mat.kd[1] / pi, t.mat.kd[2] / pi, 0.0f);
+    (*mat)[kMatStride * i + 3] = make_float4(t.n[0], t.n[1], t.n[2], 0.0f);
+    (*mat)[kMatStride * i + 4] = make_float4(t.mat.ks[0], t.mat.ks[1], t.mat.ks[2], t.area);
+  }
+}
+
+// plane groups of the brute-force mode: triangles with bit-identical (n, k) share one plane test.
+// Groups are ordered by their first triangle; slots inside a group ascend in triangle id.
+static void build_plane_groups(const HostScene& hs, std::vector<float4>* planes, std::vector<int2>* grange,
+                               std::vector<float4>* edges, std::vector<int>* slot_tri) {
+  const size_t nT = hs.tris.size();
+  std::vector<int> group_of(nT, -1);
+  std::vector<std::vector<int>> members;
+  for (size_t i = 0; i < nT; i++) {
+    const HostTriangle& t = hs.tris[i];
+    int g = -1;
+    for (size_t k = 0; k < members.size(); k++) {
+      const HostTriangle& r = hs.tris[members[k][0]];
+      if (memcmp(r.n, t.n, sizeof(t.n)) == 0 && memcmp(&r.plane_k, &t.plane_k, sizeof(float)) == 0) { g = (int)k; break; }
+    }
+    if (g < 0) { g = (int)members.size(); members.push_back(std::vector<int>()); }
+    members[g].push_back((int)i);
+  }
+  planes->clear(); grange->clear(); edges->clear(); slot_tri->clear();
+  for (size_t g = 0; g < members.size(); g++) {
+    const HostTriangle& r = hs.tris[members[g][0]];
+    planes->push_back(make_float4(r.n[0], r.n[1], r.n[2], r.plane_k));
+    int2 rg;
+    rg.x = (int)slot_tri->size();
+    for (int ti : members[g]) {
+      const HostTriangle& t = hs.tris[ti];
+      for (int j = 0; j < 3; j++) edges->push_back(make_float4(t.edge[j][0], t.edge[j][1], t.edge[j][2], t.edge[j][3]));
+      slot_tri->push_back(ti);
+    }
+    rg.y = (int)slot_tri->size();
+    grange->push_back(rg);
   }
 }
 
@@ -164,6 +205,21 @@ static int upload_scene(SceneHandle* h) {
   IPT_CUDA(cudaMemcpy(h->light, light.data(), light.size() * sizeof(float4), cudaMemcpyHostToDevice));
 
   h->use_bvh = (g_traversal_mode == 2) || (g_traversal_mode == 0 && (int)nT > kBruteForceMaxTris);
+  if (!h->use_bvh && nT) {
+    std::vector<float4> planes, edges;
+    std::vector<int2> grange;
+    std::vector<int> slot_tri;
+    build_plane_groups(hs, &planes, &grange, &edges, &slot_tri);
+    h->n_groups = (int)planes.size();
+    IPT_CUDA(cudaMalloc(&h->planes, planes.size() * sizeof(float4)));
+    IPT_CUDA(cudaMalloc(&h->grange, grange.size() * sizeof(int2)));
+    IPT_CUDA(cudaMalloc(&h->slot_edges, edges.size() * sizeof(float4)));
+    IPT_CUDA(cudaMalloc(&h->slot_tri, slot_tri.size() * sizeof(int)));
+    IPT_CUDA(cudaMemcpy(h->planes, planes.data(), planes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    IPT_CUDA(cudaMemcpy(h->grange, grange.data(), grange.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    IPT_CUDA(cudaMemcpy(h->slot_edges, edges.data(), edges.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    IPT_CUDA(cudaMemcpy(h->slot_tri, slot_tri.data(), slot_tri.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   if (h->use_bvh && nT) {
     // triangle-level tree: box = vertex bounds, split position = triangle center (the analogue of
     // Object::getBBox / getPosition, scene_basics.h:417-424, with triangles as primitives)
@@ -228,6 +284,7 @@ static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan)
   DevRender& rp = plan->rp;
   rp.width = p->width; rp.height = p->height; rp.spp = p->spp; rp.max_depth = p->max_depth;
   rp.p_rr = p->p_rr; rp.key0 = p->seed_lo; rp.key1 = p->seed_hi;
+  rp.c_diff = (1.0f / 0.318309873f) / p->p_rr;   // canon v2: diffuse coeff = cos * ((1 / (1/pi)) / p_rr), path_trace.cu:137
   rp.group_samples = (p->group_samples <= 0 || p->group_samples > p->spp) ? p->spp : p->group_samples;
   rp.groups = (p->spp + rp.group_samples - 1) / rp.group_samples;
   rp.pix_begin = rb * p->width;
@@ -387,9 +444,8 @@ int iptSetMaterialsDevice(void* scene, const float* kd_dev, void* stream) {
   if (!h || !kd_dev) return fail("iptSetMaterialsDevice: bad arguments");
   IPT_CUDA(cudaSetDevice(h->device));
   const int nT = (int)h->host.tris.size();
-  // Kd occupies xyz of every third float4: strided 2D copy, 12 bytes per row into a 48-byte pitch
-  IPT_CUDA(cudaMemcpy2DAsync(h->mat, 3 * sizeof(float4), kd_dev, 3 * sizeof(float), 3 * sizeof(float), nT, cudaMemcpyDeviceToDevice,
-                             (cudaStream_t)stream));
+  IPT_CUDA(launch_set_kd(h->mat, kd_dev, nT, (cudaStream_t)stream));
+  g_launches += 1;
   return 0;
 }
 

@@ -2,8 +2,13 @@
 //
 // HBM layout.  All arrays are float4-vectorised so one triangle test is
 // four 16-byte loads and the whole small scene can be staged into shared memory with float4 copies.
-//   geom  [4*nT] : {n.xyz, k=dot(c,n)} {e0.xyz,e0.d} {e1.xyz,e1.d} {e2.xyz,e2.d}     64 B / triangle
-//   mat   [3*nT] : {Kd.rgb, Ns} {Ke.rgb, flags(bits)} {Ks.rgb, area}                 48 B / triangle
+//   geom  [4*nT] : {n.xyz, k=dot(c,n)} {e0.xyz,e0.d} {e1.xyz,e1.d} {e2.xyz,e2.d}     64 B / triangle (BVH leaves)
+//   plane groups (brute-force mode): triangles whose (n, k) are bit-identical share one plane test
+//     planes [G]    : {n.xyz, k}                 16 B / group
+//     grange [G]    : {first slot, end slot}      8 B / group
+//     slot_edges [3*nT] : {e.xyz, e.d} x 3       48 B / slot   (slots are grouped, ascending id inside a group)
+//     slot_tri [nT] : triangle id of the slot      4 B / slot
+//   mat   [5*nT] : {Kd.rgb, Ns} {Ke.rgb, flags(bits)} {Kd/pi .rgb, 0} {n.xyz, 0} {Ks.rgb, area}   80 B / triangle
 //   light [3*nE] : {v0.xyz, cdf} {v1.xyz, p_t} {v2.xyz, tri index(bits)}             48 B / emissive
 //   vtx   [5*nT] : {v0.xyz, vn0.x} {v1.xyz, vn0.y} {v2.xyz, vn0.z} {vn1.xyz, area} {vn2.xyz, 0}
 //                  (only read for triangles that carry per-vertex normals: Triangle::getNormal)
@@ -16,8 +21,15 @@ namespace ipt {
 
 enum : int { TRI_HAS_VN = 1, TRI_SPECULAR = 2, TRI_ANY_KS = 4 };
 
+constexpr int kMatStride = 5;   // float4 records per triangle in `mat`
+
 struct DevScene {
   const float4* geom;
+  const float4* planes;
+  const int2* grange;
+  const float4* slot_edges;
+  const int* slot_tri;
+  int nGroups;
   const float4* mat;
   const float4* light;
   const float4* vtx;
@@ -31,6 +43,7 @@ struct DevScene {
 struct DevRender {
   int width, height, spp, max_depth;
   float p_rr;
+  float c_diff;         // (1 / (1/pi)) / p_rr : cosine-to-throughput factor of a diffuse bounce (canon v2)
   uint32_t key0, key1;
   int group_samples;    // samples per work item
   int groups;           // work items per pixel

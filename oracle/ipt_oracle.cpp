@@ -946,7 +946,7 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
       if (nE > 0) {
         LightSample ls;
         if (sample_light(sc, isect, un, &ls, cnt)) {
-          float g = ((ls.cos_theta * ls.cos_theta_prime) / (ls.t * ls.t)) / ls.p_t;
+          float g = (ls.cos_theta * ls.cos_theta_prime) / ((ls.t * ls.t) * ls.p_t);   // canon v2: one division
           const Triangle& t_emm = sc.tri(ls.light_tri);
           float f[3];
           bsdf(tri, isect.point, ray.d, ls.toLight, true, f);
@@ -964,7 +964,10 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
         float p_sample = sample_next_dir(tri.normal, isSpecular, tri.mat.ns, ud[0], ud[1], &nextDir);
         float f[3];
         bsdf(tri, isect.point, ray.d, nextDir, false, f);
-        float coeff = (dot(nextDir, shading_normal(tri, isect.point)) / p_sample) / P.p_rr;
+        // canon v2: the diffuse factor (1/p_sample)/p_RR is folded into one constant c_diff
+        const float c_diff = (1.0f / kInvPi) / P.p_rr;
+        float cosn = dot(nextDir, shading_normal(tri, isect.point));
+        float coeff = isSpecular ? (cosn / p_sample) / P.p_rr : cosn * c_diff;
         for (int i = 0; i < 3; i++) mult[i] = (mult[i] * f[i]) * coeff;
         vx.b = coeff / kPi;   // bookkeeping for the adjoint only (diffuse materials)
         vx.cont = true;
@@ -1071,7 +1074,7 @@ static void graph_sample(const Scene& sc, const Params& P, int r, int c, int sam
     if (nE > 0) {
       LightSample ls;
       if (sample_light(sc, isect, un, &ls, cnt)) {
-        float w = (((weight * ls.cos_theta) * ls.cos_theta_prime) / (ls.t * ls.t)) / ls.p_t;
+        float w = ((weight * ls.cos_theta) * ls.cos_theta_prime) / ((ls.t * ls.t) * ls.p_t);   // canon v2
         float f[2] = {kInvPi, 0.0f};   // BSDF(isDirect=true), inv_path_trace.cu:8,13
         edges[(size_t)tri.idx * nT + ls.light_tri].update(w, pixel, sc.tri(ls.light_tri).mat.ke, f);
       }
