@@ -148,7 +148,9 @@ static void build_plane_groups(const HostScene& hs, std::vector<float4>* planes,
     int g = -1;
     for (size_t k = 0; k < members.size(); k++) {
       const HostTriangle& r = hs.tris[members[k][0]];
-      if (memcmp(r.n, t.n, sizeof(t.n)) == 0 && memcmp(&r.plane_k, &t.plane_k, sizeof(float)) == 0) { g = (int)k; break; }
+      // value equality, so -0 and +0 components group together: a zero sign can only flip the sign of a
+      // zero denom / num, and those are rejected by |denom| <= MIN_DOT resp. t <= EPSILON either way
+      if (r.n[0] == t.n[0] && r.n[1] == t.n[1] && r.n[2] == t.n[2] && r.plane_k == t.plane_k) { g = (int)k; break; }
     }
     if (g < 0) { g = (int)members.size(); members.push_back(std::vector<int>()); }
     members[g].push_back((int)i);

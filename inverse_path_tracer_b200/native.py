@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(PKG, "lib", "libipt_b200.so")
+_LIB_PATH = os.environ.get("IPT_B200_LIB") or os.path.join(PKG, "lib", "libipt_b200.so")   # override: developer A/B builds
 
 
 class IptRenderParams(C.Structure):
