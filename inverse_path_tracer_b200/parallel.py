@@ -22,17 +22,33 @@ def scenes_for_rank(n_scenes, rank, world):
     return list(range(rank, n_scenes, world))
 
 
-def gather_rows(local, height, group=None):
-    """all-gather row blocks of unequal size into the full (height, W, 3) image on every rank"""
+def gather_rows(local, height, group=None, out=None):
+    """all-gather the row blocks into the full (height, W, 3) image on every rank.
+
+    One all_gather_into_tensor call; when height is not a multiple of the world size the blocks are
+    padded to the largest block (collectives need equal sizes) and the padding rows are dropped."""
     world = dist.get_world_size(group)
     if world == 1:
         return local
-    blocks = []
+    rank = dist.get_rank(group)
+    base, extra = divmod(height, world)
+    tail = tuple(local.shape[1:])
+    if extra == 0:
+        if out is None:
+            out = torch.empty((height,) + tail, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    mx = base + 1
+    padded = torch.zeros((mx,) + tail, dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    gathered = torch.empty((world * mx,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    parts = []
     for r in range(world):
         b, e = shard_rows(height, r, world)
-        blocks.append(torch.empty((e - b,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device))
-    dist.all_gather(blocks, local.contiguous(), group=group)
-    return torch.cat(blocks, 0)
+        parts.append(gathered[r * mx:r * mx + (e - b)])
+    assert parts[rank].shape[0] == local.shape[0]
+    return torch.cat(parts, 0)
 
 
 def render_sharded(render_rows, height, group=None):

@@ -75,5 +75,30 @@ def main():
         print("%-26s %6.1f %6.1f %6.1f" % (k, *v))
 
 
+def loader_tables():
+    """Golden loader tables from the REFERENCE's own loader (oracle/_ref/ref_loader_dump, built from
+    /root/reference by oracle/Makefile): per asset the vertex floats, triangle vertex indices and
+    per-face material ids, and the materials.  Committed as tests/golden/loader_tables.npz so the
+    loader parity test also runs where the reference tree is absent."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from oracle import oracle as O
+    O.build()
+    out = {}
+    assets = os.path.join(GOLD, "assets")
+    for key, obj, mtl in (("cornell", "CornellBox/CornellBox-Empty-CO.obj", "CornellBox/CornellBox-Empty-CO.mtl"),
+                          ("cube", "shapes/cube.obj", "/nonexistent.mtl"), ("sphere", "shapes/sphere.obj", "/nonexistent.mtl"),
+                          ("scene", "shapes/scene.obj", "/nonexistent.mtl")):
+        d = O.ref_loader_dump(os.path.join(assets, obj), os.path.join(assets, mtl) if not mtl.startswith("/") else mtl)
+        out[key + "_V"] = d["V"]
+        out[key + "_N"] = d["N"]
+        out[key + "_F"] = d["F"]
+        out[key + "_M"] = np.array([m["kd"] + m["ks"] + m["ke"] + [m["ns"], m["ni"], m["d"], float(m["illum"])] for m in d["M"]],
+                                   np.float32).reshape(-1, 13)
+        out[key + "_Mnames"] = np.array([m["name"] for m in d["M"]])
+    np.savez_compressed(os.path.join(GOLD, "loader_tables.npz"), **out)
+    print("loader tables:", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     main()
+    loader_tables()
