@@ -71,6 +71,7 @@ struct SceneHandle {
   float4* slot_edges = nullptr;
   int* slot_tri = nullptr;
   int n_groups = 0;
+  int n_slots = 0;
   float4* mat = nullptr;
   float4* light = nullptr;
   float4* vtx = nullptr;
@@ -89,7 +90,7 @@ struct SceneHandle {
 
   DevScene dev() const {
     DevScene d;
-    d.geom = geom; d.planes = planes; d.grange = grange; d.slot_edges = slot_edges; d.slot_tri = slot_tri; d.nGroups = n_groups; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_prims = bvh_prims;
+    d.geom = geom; d.planes = planes; d.grange = grange; d.slot_edges = slot_edges; d.slot_tri = slot_tri; d.nGroups = n_groups; d.nSlots = n_slots; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_prims = bvh_prims;
     d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.use_bvh = use_bvh ? 1 : 0;
     memcpy(d.cam, host.cam, sizeof(d.cam));
     return d;
@@ -166,6 +167,12 @@ static void build_plane_groups(const HostScene& hs, std::vector<float4>* planes,
       for (int j = 0; j < 3; j++) edges->push_back(make_float4(t.edge[j][0], t.edge[j][1], t.edge[j][2], t.edge[j][3]));
       slot_tri->push_back(ti);
     }
+    if ((slot_tri->size() - (size_t)rg.x) & 1) {
+      // pad the group to an even number of slots with a triangle nothing can hit (edge offset +inf -> sd = +inf > 0),
+      // so the kernel's inner loop always handles two slots per trip without a remainder path
+      for (int j = 0; j < 3; j++) edges->push_back(make_float4(0.0f, 0.0f, 0.0f, INFINITY));
+      slot_tri->push_back(-1);
+    }
     rg.y = (int)slot_tri->size();
     grange->push_back(rg);
   }
@@ -213,6 +220,7 @@ static int upload_scene(SceneHandle* h) {
     std::vector<int> slot_tri;
     build_plane_groups(hs, &planes, &grange, &edges, &slot_tri);
     h->n_groups = (int)planes.size();
+    h->n_slots = (int)slot_tri.size();
     IPT_CUDA(cudaMalloc(&h->planes, planes.size() * sizeof(float4)));
     IPT_CUDA(cudaMalloc(&h->grange, grange.size() * sizeof(int2)));
     IPT_CUDA(cudaMalloc(&h->slot_edges, edges.size() * sizeof(float4)));

@@ -30,6 +30,7 @@ struct DevScene {
   const float4* slot_edges;
   const int* slot_tri;
   int nGroups;
+  int nSlots;             // >= nT: groups are padded to an even slot count
   const float4* mat;
   const float4* light;
   const float4* vtx;
