@@ -116,6 +116,10 @@ int iptSetMaterialsDevice(void* scene, const float* kd_dev, void* stream);
 int iptBuildBVH(const float* boxes, const float* pos, int n, int leaf_size, float* node_boxes, int* node_ints,
                 int max_nodes, int* perm);
 
+/* builder used by iptBuildBVH and by BVH-mode scene loads: 0 = auto (CUDA kernels from 2048 primitives
+ * on, one host thread below), 1 = host, 2 = CUDA kernels.  All produce bit-identical trees. */
+int iptSetBvhBuilder(int mode);
+
 int iptWritePNG(const char* path, const unsigned char* rgb, int width, int height);
 int iptReadPNG(const char* path, unsigned char* rgb, int capacity_bytes, int* width, int* height);
 

@@ -362,7 +362,12 @@ int iptSetTraversalMode(int mode) {
   g_traversal_mode = mode;
   return 0;
 }
-unsigned long long iptKernelLaunchCount(void) { return g_launches.load(); }
+unsigned long long iptKernelLaunchCount(void) { return g_launches.load() + bvh_kernel_launches(); }
+int iptSetBvhBuilder(int mode) {
+  if (mode < 0 || mode > 2) return fail("BVH builder mode must be 0 (auto), 1 (host) or 2 (GPU)");
+  set_bvh_builder_mode(mode);
+  return 0;
+}
 
 int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mtl_fs, int n, void** scenePtr) {
   if (scenePtr) *scenePtr = nullptr;
@@ -816,7 +821,7 @@ int iptBuildBVH(const float* boxes, const float* pos, int n, int leaf_size, floa
   std::vector<int> pm;
   std::string err;
   int dev = g_device;
-  if (dev < 0) cudaGetDevice(&dev);
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) dev = -1;
   if (!build_bvh(boxes, pos, n, leaf_size, &nodes, &pm, dev, &err)) return fail(err);
   if ((int)nodes.size() > max_nodes) return fail("iptBuildBVH: max_nodes too small");
   for (size_t i = 0; i < nodes.size(); i++) {

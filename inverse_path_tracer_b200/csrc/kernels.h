@@ -28,6 +28,8 @@ struct BvhNodeHost {
   float lo[3], hi[3];
   int start, nPrims, rightOffset;
 };
+void set_bvh_builder_mode(int mode);   // 0 auto, 1 host, 2 GPU
+unsigned long long bvh_kernel_launches();
 bool build_bvh(const float* boxes, const float* pos, int n, int leaf_size, std::vector<BvhNodeHost>* nodes, std::vector<int>* perm,
                int device, std::string* err);
 

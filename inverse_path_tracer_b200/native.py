@@ -31,7 +31,7 @@ EXPORTS = ["loadScene", "freeScene", "createImage", "createGraph", "getMaterials
            "iptSceneInfo", "iptGetTriangleTable", "iptGetCamera", "iptTraceRays", "iptTraceRaysDevice",
            "iptRender", "iptRenderDevice", "iptCreateImageEx", "iptCreateGraphEx", "iptGraphAccumulateDevice",
            "iptGraphCompress", "iptRenderGrad", "iptRenderGradDevice", "iptSetMaterialsDevice", "iptBuildBVH",
-           "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters"]
+           "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder"]
 
 
 def lib():
@@ -101,8 +101,10 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def build_bvh(boxes, pos, leaf_size=4):
-    """GPU-side restatement of BVH::build (bvh.h:109-205) on caller primitives -> (node_boxes, node_ints, perm)."""
+def build_bvh(boxes, pos, leaf_size=4, builder=0):
+    """BVH::build (bvh.h:109-205) on caller primitives -> (node_boxes, node_ints, perm).
+    builder: 0 auto (CUDA kernels from 2048 primitives on), 1 host, 2 CUDA kernels."""
+    lib().iptSetBvhBuilder(int(builder))
     boxes = np.ascontiguousarray(boxes, np.float32).reshape(-1, 6)
     pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
     n = boxes.shape[0]
@@ -111,6 +113,7 @@ def build_bvh(boxes, pos, leaf_size=4):
     ni = np.zeros((mx, 3), np.int32)
     perm = np.zeros(max(n, 1), np.int32)
     k = lib().iptBuildBVH(_ptr(boxes), _ptr(pos), n, leaf_size, _ptr(nb), _ptr(ni), mx, _ptr(perm))
+    lib().iptSetBvhBuilder(0)
     if k < 0:
         raise RuntimeError("iptBuildBVH failed: " + last_error())
     return nb[:k], ni[:k], perm[:n]

@@ -584,13 +584,19 @@ static void bvh_build(const Box* boxes, const V3* pos, int n, int leaf_size, std
     node.start = start;
     node.nPrims = nPrims;
     node.rightOffset = UNTOUCHED;
+    // min / max under the total order -0 < +0 (order-independent, so a parallel reduction gives the same bits;
+    // the reference's CMIN/CMAX, scene_basics.h:30-31, leave the sign of a zero bound to evaluation order)
+    auto tmin = [](float a, float b) { return (b < a || (b == a && std::signbit(b))) ? b : a; };
+    auto tmax = [](float a, float b) { return (b > a || (b == a && !std::signbit(b))) ? b : a; };
+    auto tmin3 = [&](V3 a, V3 b) { return mk(tmin(a.x, b.x), tmin(a.y, b.y), tmin(a.z, b.z)); };
+    auto tmax3 = [&](V3 a, V3 b) { return mk(tmax(a.x, b.x), tmax(a.y, b.y), tmax(a.z, b.z)); };
     Box bb = boxes[p[start]];
     V3 clo = pos[p[start]], chi = pos[p[start]];
     for (int q = start + 1; q < end; q++) {
-      bb.lo = vmin(bb.lo, boxes[p[q]].lo);
-      bb.hi = vmax(bb.hi, boxes[p[q]].hi);
-      clo = vmin(clo, pos[p[q]]);
-      chi = vmax(chi, pos[p[q]]);
+      bb.lo = tmin3(bb.lo, boxes[p[q]].lo);
+      bb.hi = tmax3(bb.hi, boxes[p[q]].hi);
+      clo = tmin3(clo, pos[p[q]]);
+      chi = tmax3(chi, pos[p[q]]);
     }
     node.lo[0] = bb.lo.x; node.lo[1] = bb.lo.y; node.lo[2] = bb.lo.z;
     node.hi[0] = bb.hi.x; node.hi[1] = bb.hi.y; node.hi[2] = bb.hi.z;

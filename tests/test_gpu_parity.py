@@ -216,3 +216,33 @@ def test_legacy_abi_roundtrip(ipt, oracle, tmp_path, monkeypatch):
     out = str(tmp_path / "pred.png")
     ipt_cuda.render_with_materials(scenefile, out, np.full((30, 3), 0.5, np.float32))
     assert np.asarray(Image.open(out)).shape == (500, 500, 3)
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (5, 2), (9, 3), (64, 4), (1000, 5), (4097, 6), (50000, 7), (1000000, 8)])
+def test_gpu_bvh_builder_layout_bit_exact(ipt, oracle, n, seed):
+    """the CUDA builder (level-synchronous, closed-form Lomuto permutation) against the oracle's sequential bvh.h restatement"""
+    from inverse_path_tracer_b200 import native
+    rng = np.random.RandomState(seed)
+    pos = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
+    ext = rng.uniform(0, 0.3, (n, 3)).astype(np.float32)
+    boxes = np.concatenate([pos - ext, pos + ext], 1).astype(np.float32)
+    nb_g, ni_g, perm_g = native.build_bvh(boxes, pos, builder=2)
+    nb_o, ni_o, perm_o = oracle.bvh_build(boxes, pos)
+    assert np.array_equal(perm_g, perm_o) and np.array_equal(ni_g, ni_o) and nb_g.tobytes() == nb_o.tobytes()
+
+
+def test_gpu_bvh_builder_degenerate_and_scene_inputs(ipt, oracle):
+    from inverse_path_tracer_b200 import native
+    rng = np.random.RandomState(9)
+    grid = np.stack(np.meshgrid(np.arange(16), np.arange(15), np.arange(14), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    dup = rng.uniform(-1, 1, (700, 3)).astype(np.float32)
+    line = np.zeros((5000, 3), np.float32)
+    line[:, 1] = np.repeat(np.arange(100), 50)
+    zeros = np.array([[0.0, -0.0, 0.0], [-0.0, 0.0, 1.0], [0.0, 0.0, -0.0], [-0.0, -0.0, 2.0], [1.0, 0.0, 0.0], [-0.0, 1.0, -0.0]], np.float32)
+    cases = [np.tile(np.array([[1.0, 2.0, 3.0]], np.float32), (3700, 1)), grid, rng.permutation(grid), line, np.concatenate([dup, dup, dup[:70]]), zeros]
+    o = oracle.OracleScene(scene_objects("cornell_sphere"), ASSETS)
+    t = o.triangle_table()
+    for pos in cases + [t["center"]]:
+        boxes = np.concatenate([pos - 0.01, pos + 0.02], 1).astype(np.float32) if pos is not t["center"] else np.concatenate([t["verts"].min(1), t["verts"].max(1)], 1)
+        a, b = native.build_bvh(boxes, pos, builder=2), oracle.bvh_build(boxes, pos)
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1]) and a[0].tobytes() == b[0].tobytes()

@@ -67,6 +67,16 @@ def test_set_get_materials_roundtrip_and_handle_validation(ipt):
     g.h = C.c_void_p(0)
 
 
+def test_gpu_builder_is_required_for_large_inputs_without_a_device(ipt):
+    import torch
+    from inverse_path_tracer_b200 import native
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    pos = np.random.RandomState(0).uniform(-1, 1, (3000, 3)).astype(np.float32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        native.build_bvh(np.concatenate([pos, pos], 1), pos)          # auto: >= 2048 primitives -> CUDA kernels
+
+
 def test_no_cpu_fallback(ipt):
     g = _host_scene(ipt, scene_objects("cornell"))
     p = ipt.default_params(width=8, height=8, spp=1)
@@ -103,7 +113,7 @@ def test_bvh_builder_layout_bit_exact_vs_oracle(ipt, oracle, n, seed):
     pos = rng.uniform(-3, 3, (n, 3)).astype(np.float32)
     ext = rng.uniform(0, 0.3, (n, 3)).astype(np.float32)
     boxes = np.concatenate([pos - ext, pos + ext], 1).astype(np.float32)
-    nb_g, ni_g, perm_g = native.build_bvh(boxes, pos)
+    nb_g, ni_g, perm_g = native.build_bvh(boxes, pos, builder=1)   # host execution (CPU suite); the CUDA kernels: test_gpu_parity.py
     nb_o, ni_o, perm_o = oracle.bvh_build(boxes, pos)
     assert np.array_equal(perm_g, perm_o) and np.array_equal(ni_g, ni_o) and nb_g.tobytes() == nb_o.tobytes()
 
@@ -124,8 +134,13 @@ def test_bvh_builder_degenerate_inputs(ipt, oracle):
     cases.append(np.concatenate([dup, dup, dup[:7]]))                                     # duplicates
     for pos in cases:
         boxes = np.concatenate([pos - 0.01, pos + 0.02], 1).astype(np.float32)
-        a, b = native.build_bvh(boxes, pos), oracle.bvh_build(boxes, pos)
+        a, b = native.build_bvh(boxes, pos, builder=1), oracle.bvh_build(boxes, pos)
         assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1]) and a[0].tobytes() == b[0].tobytes()
+    # signed zeros: bounds are reduced under the total order -0 < +0
+    pos = np.array([[0.0, -0.0, 0.0], [-0.0, 0.0, 1.0], [0.0, 0.0, -0.0], [-0.0, -0.0, 2.0], [1.0, 0.0, 0.0], [-0.0, 1.0, -0.0]], np.float32)
+    boxes = np.concatenate([pos, pos], 1)
+    a, b = native.build_bvh(boxes, pos, builder=1), oracle.bvh_build(boxes, pos)
+    assert a[0].tobytes() == b[0].tobytes() and np.array_equal(a[2], b[2])
 
 
 def test_bvh_builder_on_scene_triangles_and_objects(ipt, oracle):
@@ -133,7 +148,7 @@ def test_bvh_builder_on_scene_triangles_and_objects(ipt, oracle):
     o = oracle.OracleScene(scene_objects("cornell_sphere"), ASSETS)
     t = o.triangle_table()
     boxes = np.concatenate([t["verts"].min(1), t["verts"].max(1)], 1)
-    a, b = native.build_bvh(boxes, t["center"]), oracle.bvh_build(boxes, t["center"])
+    a, b = native.build_bvh(boxes, t["center"], builder=1), oracle.bvh_build(boxes, t["center"])
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1]) and a[0].tobytes() == b[0].tobytes()
     ob, op = oracle.OracleScene(scene_objects("rotated_cubes"), ASSETS).object_prims()     # 5 objects > leafSize: a real split
     a, b = native.build_bvh(ob, op), oracle.bvh_build(ob, op)
