@@ -22,6 +22,7 @@
 #include "device_scene.h"
 #include "kernels.h"
 #include "scene_host.h"
+#include "ipt_math.cuh"
 
 namespace ipt {
 
@@ -125,7 +126,8 @@ static void pack_materials(const HostScene& hs, std::vector<float4>* mat) {
   for (size_t i = 0; i < nT; i++) {
     const HostTriangle& t = hs.tris[i];
     const bool any_ks = t.mat.ks[0] != 0.0f || t.mat.ks[1] != 0.0f || t.mat.ks[2] != 0.0f;
-    int flags = (t.has_vn ? TRI_HAS_VN : 0) | (any_ks ? TRI_ANY_KS : 0) | ((any_ks && t.mat.ns != 0.0f) ? TRI_SPECULAR : 0);   // path_trace.cu:132
+    int flags = (t.has_vn ? TRI_HAS_VN : 0) | (any_ks ? TRI_ANY_KS : 0) | ((any_ks && t.mat.ns != 0.0f) ? TRI_SPECULAR : 0) |   // path_trace.cu:132
+                (t.n[2] == -1.0f ? TRI_NEG_Z : 0);
     float fbits;
     memcpy(&fbits, &flags, 4);
     const float pi = 3.14159274f;   // (float)M_PI; Kd / pi is the indirect BSDF (path_trace.cu:15-17), divided once here
@@ -134,6 +136,11 @@ static void pack_materials(const HostScene& hs, std::vector<float4>* mat) {
     (*mat)[kMatStride * i + 2] = make_float4(t.mat.kd[0] / pi, t.mat.kd[1] / pi, t.mat.kd[2] / pi, 0.0f);
     (*mat)[kMatStride * i + 3] = make_float4(t.n[0], t.n[1], t.n[2], 0.0f);
     (*mat)[kMatStride * i + 4] = make_float4(t.mat.ks[0], t.mat.ks[1], t.mat.ks[2], t.area);
+    float R[9];
+    frame_rows_from_z(mk3(t.n[0], t.n[1], t.n[2]), R);   // sampleNextDir's rotation, fixed per triangle
+    (*mat)[kMatStride * i + 5] = make_float4(R[0], R[1], R[2], 0.0f);
+    (*mat)[kMatStride * i + 6] = make_float4(R[3], R[4], R[5], 0.0f);
+    (*mat)[kMatStride * i + 7] = make_float4(R[6], R[7], R[8], 0.0f);
   }
 }
 
@@ -294,6 +301,9 @@ static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan)
   DevRender& rp = plan->rp;
   rp.width = p->width; rp.height = p->height; rp.spp = p->spp; rp.max_depth = p->max_depth;
   rp.p_rr = p->p_rr; rp.key0 = p->seed_lo; rp.key1 = p->seed_hi;
+  rp.inv_spp = 1.0f / (float)p->spp;
+  rp.two_over_w = 2.0f / (float)p->width;
+  rp.two_over_h = 2.0f / (float)p->height;
   rp.c_diff = (1.0f / 0.318309873f) / p->p_rr;   // canon v2: diffuse coeff = cos * ((1 / (1/pi)) / p_rr), path_trace.cu:137
   rp.group_samples = (p->group_samples <= 0 || p->group_samples > p->spp) ? p->spp : p->group_samples;
   rp.groups = (p->spp + rp.group_samples - 1) / rp.group_samples;

@@ -8,7 +8,8 @@
 //     grange [G]    : {first slot, end slot}      8 B / group
 //     slot_edges [3*nT] : {e.xyz, e.d} x 3       48 B / slot   (slots are grouped, ascending id inside a group)
 //     slot_tri [nT] : triangle id of the slot      4 B / slot
-//   mat   [5*nT] : {Kd.rgb, Ns} {Ke.rgb, flags(bits)} {Kd/pi .rgb, 0} {n.xyz, 0} {Ks.rgb, area}   80 B / triangle
+//   mat   [8*nT] : {Kd.rgb, Ns} {Ke.rgb, flags(bits)} {Kd/pi .rgb, 0} {n.xyz, 0} {Ks.rgb, area}
+//                  {R row0, 0} {R row1, 0} {R row2, 0}   (R = FromTwoVectors(z, n), path_trace.cu:102)   128 B / triangle
 //   light [3*nE] : {v0.xyz, cdf} {v1.xyz, p_t} {v2.xyz, tri index(bits)}             48 B / emissive
 //   vtx   [5*nT] : {v0.xyz, vn0.x} {v1.xyz, vn0.y} {v2.xyz, vn0.z} {vn1.xyz, area} {vn2.xyz, 0}
 //                  (only read for triangles that carry per-vertex normals: Triangle::getNormal)
@@ -19,9 +20,9 @@
 
 namespace ipt {
 
-enum : int { TRI_HAS_VN = 1, TRI_SPECULAR = 2, TRI_ANY_KS = 4 };
+enum : int { TRI_HAS_VN = 1, TRI_SPECULAR = 2, TRI_ANY_KS = 4, TRI_NEG_Z = 8 /* normal.z == -1: R = -I, path_trace.cu:99-100 */ };
 
-constexpr int kMatStride = 5;   // float4 records per triangle in `mat`
+constexpr int kMatStride = 8;   // float4 records per triangle in `mat`
 
 struct DevScene {
   const float4* geom;
@@ -45,6 +46,8 @@ struct DevRender {
   int width, height, spp, max_depth;
   float p_rr;
   float c_diff;         // (1 / (1/pi)) / p_rr : cosine-to-throughput factor of a diffuse bounce (canon v2)
+  float inv_spp;        // 1 / spp (canon v3: toneMap's src[i]/SPP as a product)
+  float two_over_w, two_over_h;   // camera raster scale (canon v3)
   uint32_t key0, key1;
   int group_samples;    // samples per work item
   int groups;           // work items per pixel

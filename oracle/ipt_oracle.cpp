@@ -99,14 +99,28 @@ static inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], u
 // curand_uniform maps a 32-bit draw to (0,1]:  x*2^-32 + 2^-33  (curand_uniform.h); canon fuses it.
 static inline float u01(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
 
-enum { STREAM_CAMERA = 0, STREAM_NEE_RR = 1, STREAM_DIR = 2 };
+// 16 random bits -> (0,1):  x*2^-16 + 2^-17  (canon v3: light pick, RR, and the light-point pair share words)
+static inline float u16(uint32_t x) { return fmaf((float)x, 1.52587890625e-05f, 7.62939453125e-06f); }
+
+enum { STREAM_CAMERA = 0, STREAM_BOUNCE = 1 };
 struct Rng {
   uint32_t key[2];
   uint32_t pixel, sample;
-  void draw(uint32_t bounce, uint32_t stream, float u[4]) const {
-    uint32_t ctr[4] = {pixel, sample, bounce, stream}, o[4];
+  // camera stream: u[0], u[1] = pixel jitter (32-bit uniforms)
+  void draw_camera(float u[2]) const {
+    uint32_t ctr[4] = {pixel, sample, 0u, STREAM_CAMERA}, o[4];
     philox4x32_10(ctr, key, o);
-    for (int i = 0; i < 4; i++) u[i] = u01(o[i]);
+    u[0] = u01(o[0]); u[1] = u01(o[1]);
+  }
+  // one Philox call per bounce (canon v3), in the reference's draw order (path_trace.cu:43,55-56,130,93-94):
+  //   word0 = [light pick : 16 | Russian roulette : 16], word1 = [r1 : 16 | r2 : 16], word2 = phi, word3 = theta
+  // un = {pick, r1, r2, rr}, ud = {phi, theta}
+  void draw_bounce(uint32_t bounce, float un[4], float ud[2]) const {
+    uint32_t ctr[4] = {pixel, sample, bounce, STREAM_BOUNCE}, o[4];
+    philox4x32_10(ctr, key, o);
+    un[0] = u16(o[0] >> 16); un[3] = u16(o[0] & 0xffffu);
+    un[1] = u16(o[1] >> 16); un[2] = u16(o[1] & 0xffffu);
+    ud[0] = u01(o[2]); ud[1] = u01(o[3]);
   }
 };
 
@@ -896,14 +910,15 @@ static bool sample_light(const Scene& sc, const Hit& isect, const float u[3], Li
 
 // camera ray, path_trace.cu:155-165 + Ray::transform scene_basics.h:307-319
 static Ray camera_ray(const Scene& sc, const Params& P, int r, int c, float ux, float uy) {
-  float x = (2.0f * ((float)c + ux)) / (float)P.width - 1.0f;
-  float y = 1.0f - (2.0f * ((float)r + uy)) / (float)P.height;
-  V3 d = normalize(mk(x, y, 1.0f));
-  V3 p = mk(0, 0, 0);
+  // canon v3: x = (c+u)*(2/W) - 1, y = 1 - (r+u)*(2/H) with the two quotients formed once; the direction
+  // is normalised once, after the camera matrix (the reference normalises before and after; same direction)
+  const float two_over_w = 2.0f / (float)P.width, two_over_h = 2.0f / (float)P.height;
+  float x = fmaf((float)c + ux, two_over_w, -1.0f);
+  float y = fmaf((float)r + uy, -two_over_h, 1.0f);
+  V3 d = mk(x, y, 1.0f);
   const float(*M)[4] = sc.cam.M;
   Ray ray;
-  ray.p = mk(dot(mk(M[0][0], M[0][1], M[0][2]), p) + M[0][3], dot(mk(M[1][0], M[1][1], M[1][2]), p) + M[1][3],
-             dot(mk(M[2][0], M[2][1], M[2][2]), p) + M[2][3]);
+  ray.p = mk(M[0][3], M[1][3], M[2][3]);   // M * (0,0,0,1)
   ray.d = normalize(mk(dot(mk(M[0][0], M[0][1], M[0][2]), d), dot(mk(M[1][0], M[1][1], M[1][2]), d), dot(mk(M[2][0], M[2][1], M[2][2]), d)));
   return ray;
 }
@@ -925,8 +940,8 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
   rng.key[0] = P.seed_lo; rng.key[1] = P.seed_hi;
   rng.pixel = (uint32_t)(r * P.width + c);
   rng.sample = (uint32_t)sample;
-  float u[4];
-  rng.draw(0, STREAM_CAMERA, u);
+  float u[2];
+  rng.draw_camera(u);
   Ray ray = camera_ray(sc, P, r, c, u[0], u[1]);
   L[0] = L[1] = L[2] = 0.0f;
   float L_e[3] = {0, 0, 0}, L_d[3] = {0, 0, 0};
@@ -946,8 +961,8 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
       vx.tri = tri.idx;
       if (recursion == 0) for (int i = 0; i < 3; i++) L_e[i] = tri.mat.ke[i];
       // directLighting, path_trace.cu:30-89
-      float un[4];
-      rng.draw((uint32_t)recursion, STREAM_NEE_RR, un);
+      float un[4], ud[2];
+      rng.draw_bounce((uint32_t)recursion, un, ud);
       L_d[0] = L_d[1] = L_d[2] = 0.0f;
       if (nE > 0) {
         LightSample ls;
@@ -963,8 +978,6 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
       }
       // Russian roulette + continuation, path_trace.cu:130-141
       if (un[3] < P.p_rr) {
-        float ud[4];
-        rng.draw((uint32_t)recursion, STREAM_DIR, ud);
         bool isSpecular = has_specular(tri.mat) && tri.mat.ns != 0.0f;
         V3 nextDir;
         float p_sample = sample_next_dir(tri.normal, isSpecular, tri.mat.ns, ud[0], ud[1], &nextDir);
@@ -997,13 +1010,14 @@ static inline int group_size(const Params& P) { return (P.group_samples <= 0 || 
 // `group_samples` consecutive samples; group partials are then added in group order.
 static void render_pixel(const Scene& sc, const Params& P, int r, int c, float out[3], Counters* cnt) {
   const int gs = group_size(P);
+  const float inv_spp = 1.0f / (float)P.spp;   // canon v3: src[i] * (1/SPP) (exact for power-of-two SPP)
   float total[3] = {0, 0, 0};
   for (int g0 = 0; g0 < P.spp; g0 += gs) {
     float part[3] = {0, 0, 0};
     for (int s = g0; s < std::min(P.spp, g0 + gs); s++) {
       float L[3];
       render_sample(sc, P, r, c, s, L, cnt, nullptr);
-      for (int i = 0; i < 3; i++) part[i] += L[i] / (float)P.spp;
+      for (int i = 0; i < 3; i++) part[i] += L[i] * inv_spp;
     }
     if (g0 == 0) for (int i = 0; i < 3; i++) total[i] = part[i];
     else for (int i = 0; i < 3; i++) total[i] += part[i];
@@ -1054,8 +1068,8 @@ static void graph_sample(const Scene& sc, const Params& P, int r, int c, int sam
   rng.key[0] = P.seed_lo; rng.key[1] = P.seed_hi;
   rng.pixel = (uint32_t)(r * P.width + c);
   rng.sample = (uint32_t)sample;
-  float u[4];
-  rng.draw(0, STREAM_CAMERA, u);
+  float u[2];
+  rng.draw_camera(u);
   Ray ray = camera_ray(sc, P, r, c, u[0], u[1]);
   float weight = 1.0f;
   float factors[2] = {1.0f, 1.0f};
@@ -1071,10 +1085,9 @@ static void graph_sample(const Scene& sc, const Params& P, int r, int c, int sam
     cnt->ext_rays++;
     if (isect.tri < 0) break;
     const Triangle& tri = sc.tri(isect.tri);
-    float un[4], ud[4];
-    rng.draw((uint32_t)recursion, STREAM_NEE_RR, un);
-    rng.draw((uint32_t)recursion, STREAM_DIR, ud);
-    bool isSpecular = ud[2] < kPSpec;   // always false
+    float un[4], ud[2];
+    rng.draw_bounce((uint32_t)recursion, un, ud);
+    bool isSpecular = false;   // curand_uniform(&state) < P_SPEC with P_SPEC == 0 (inv_path_trace.cu:117): never true, not drawn
     int src = tri.idx;
     edges[(size_t)dst * nT + src].update(weight, pixel, zero, factors);
     if (nE > 0) {
@@ -1379,9 +1392,11 @@ void orc_object_prims(void* h, float* boxes, float* pos) {
 int orc_num_objects(void* h) { return (int)((Scene*)h)->objects.size(); }
 
 void orc_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
+// stream 0: u[0..1] = camera jitter; stream 1: u[0..3] = pick, r1, r2, rr and u[4..5] = phi, theta
 void orc_uniforms(uint32_t seed_lo, uint32_t seed_hi, uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t stream, float* u) {
   Rng r; r.key[0] = seed_lo; r.key[1] = seed_hi; r.pixel = pixel; r.sample = sample;
-  r.draw(bounce, stream, u);
+  if (stream == STREAM_CAMERA) r.draw_camera(u);
+  else r.draw_bounce(bounce, u, u + 4);
 }
 void orc_sincos2pi(float u, float* s, float* c) { sincos2pi(u, s, c); }
 void orc_sample_dir(const float* n, float u_phi, float u_theta, float* out) {

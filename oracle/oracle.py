@@ -210,7 +210,7 @@ def philox(ctr, key):
 
 
 def uniforms(seed, pixel, sample, bounce, stream):
-    u = np.zeros(4, np.float32)
+    u = np.zeros(6, np.float32)
     lib().orc_uniforms(C.c_uint32(seed & 0xFFFFFFFF), C.c_uint32(seed >> 32), C.c_uint32(pixel), C.c_uint32(sample),
                        C.c_uint32(bounce), C.c_uint32(stream), _ptr(u))
     return u
