@@ -70,7 +70,7 @@ struct SceneHandle {
   float4* planes = nullptr;
   int2* grange = nullptr;
   float4* slot_edges = nullptr;
-  int* slot_tri = nullptr;
+  int2* slot_tri = nullptr;
   int n_groups = 0;
   int n_slots = 0;
   float4* mat = nullptr;
@@ -131,25 +131,31 @@ static void pack_materials(const HostScene& hs, std::vector<float4>* mat) {
     float fbits;
     memcpy(&fbits, &flags, 4);
     const float pi = 3.14159274f;   // (float)M_PI; Kd / pi is the indirect BSDF (path_trace.cu:15-17), divided once here
-    (*mat)[kMatStride * i + 0] = make_float4(t.mat.kd[0], t.mat.kd[1], t.mat.kd[2], t.mat.ns);
-    (*mat)[kMatStride * i + 1] = make_float4(t.mat.ke[0], t.mat.ke[1], t.mat.ke[2], fbits);
-    (*mat)[kMatStride * i + 2] = make_float4(t.mat.kd[0] / pi, t.mat.kd[1] / pi, t.mat.kd[2] / pi, 0.0f);
-    (*mat)[kMatStride * i + 3] = make_float4(t.n[0], t.n[1], t.n[2], 0.0f);
-    (*mat)[kMatStride * i + 4] = make_float4(t.mat.ks[0], t.mat.ks[1], t.mat.ks[2], t.area);
+    (*mat)[0 * nT + i] = make_float4(t.mat.kd[0], t.mat.kd[1], t.mat.kd[2], t.mat.ns);
+    (*mat)[1 * nT + i] = make_float4(t.mat.ke[0], t.mat.ke[1], t.mat.ke[2], fbits);
+    (*mat)[2 * nT + i] = make_float4(t.mat.kd[0] / pi, t.mat.kd[1] / pi, t.mat.kd[2] / pi, 0.0f);
+    (*mat)[3 * nT + i] = make_float4(t.n[0], t.n[1], t.n[2], 0.0f);
+    (*mat)[4 * nT + i] = make_float4(t.mat.ks[0], t.mat.ks[1], t.mat.ks[2], t.area);
     float R[9];
     frame_rows_from_z(mk3(t.n[0], t.n[1], t.n[2]), R);   // sampleNextDir's rotation, fixed per triangle
-    (*mat)[kMatStride * i + 5] = make_float4(R[0], R[1], R[2], 0.0f);
-    (*mat)[kMatStride * i + 6] = make_float4(R[3], R[4], R[5], 0.0f);
-    (*mat)[kMatStride * i + 7] = make_float4(R[6], R[7], R[8], 0.0f);
+    (*mat)[5 * nT + i] = make_float4(R[0], R[1], R[2], 0.0f);
+    (*mat)[6 * nT + i] = make_float4(R[3], R[4], R[5], 0.0f);
+    (*mat)[7 * nT + i] = make_float4(R[6], R[7], R[8], 0.0f);
   }
 }
 
-// plane groups of the brute-force mode: triangles with bit-identical (n, k) share one plane test.
-// Groups are ordered by their first triangle; slots inside a group ascend in triangle id.
+// plane groups of the brute-force mode: triangles with value-equal (n, k) share one plane test.  Inside a
+// group, two triangles whose shared edge carries exactly negated edge planes (the two halves of a quad:
+// out_b = -out_a and d_b = -d_a bit for bit, so sd_b = -sd_a exactly) are paired into one QUAD SLOT of five
+// edge records {diag (a's sign), a's other two edges, b's other two edges}; the kernel evaluates five edge
+// planes for the two triangles instead of six.  An unpaired triangle occupies a slot whose second half
+// can never be hit (edge offset +inf, id -1).  Groups are ordered by their first triangle.
+static bool edges_negated(const float* ea, const float* eb) {
+  return ea[0] == -eb[0] && ea[1] == -eb[1] && ea[2] == -eb[2] && ea[3] == -eb[3];
+}
 static void build_plane_groups(const HostScene& hs, std::vector<float4>* planes, std::vector<int2>* grange,
-                               std::vector<float4>* edges, std::vector<int>* slot_tri) {
+                               std::vector<float4>* edges, std::vector<int2>* slot_ids) {
   const size_t nT = hs.tris.size();
-  std::vector<int> group_of(nT, -1);
   std::vector<std::vector<int>> members;
   for (size_t i = 0; i < nT; i++) {
     const HostTriangle& t = hs.tris[i];
@@ -163,24 +169,44 @@ static void build_plane_groups(const HostScene& hs, std::vector<float4>* planes,
     if (g < 0) { g = (int)members.size(); members.push_back(std::vector<int>()); }
     members[g].push_back((int)i);
   }
-  planes->clear(); grange->clear(); edges->clear(); slot_tri->clear();
+  planes->clear(); grange->clear(); edges->clear(); slot_ids->clear();
+  auto push_edge = [&](const float* e) { edges->push_back(make_float4(e[0], e[1], e[2], e[3])); };
+  const float never[4] = {0.0f, 0.0f, 0.0f, INFINITY};
   for (size_t g = 0; g < members.size(); g++) {
     const HostTriangle& r = hs.tris[members[g][0]];
     planes->push_back(make_float4(r.n[0], r.n[1], r.n[2], r.plane_k));
     int2 rg;
-    rg.x = (int)slot_tri->size();
-    for (int ti : members[g]) {
-      const HostTriangle& t = hs.tris[ti];
-      for (int j = 0; j < 3; j++) edges->push_back(make_float4(t.edge[j][0], t.edge[j][1], t.edge[j][2], t.edge[j][3]));
-      slot_tri->push_back(ti);
+    rg.x = (int)slot_ids->size();
+    std::vector<char> used(members[g].size(), 0);
+    for (size_t ia = 0; ia < members[g].size(); ia++) {
+      if (used[ia]) continue;
+      used[ia] = 1;
+      const HostTriangle& ta = hs.tris[members[g][ia]];
+      int partner = -1, ja = -1, jb = -1;
+      for (size_t ib = ia + 1; ib < members[g].size() && partner < 0; ib++) {
+        if (used[ib]) continue;
+        const HostTriangle& tb = hs.tris[members[g][ib]];
+        for (int x = 0; x < 3 && partner < 0; x++)
+          for (int y = 0; y < 3; y++)
+            if (edges_negated(ta.edge[x], tb.edge[y])) { partner = (int)ib; ja = x; jb = y; break; }
+      }
+      int2 ids;
+      ids.x = ta.idx;
+      if (partner >= 0) {
+        used[partner] = 1;
+        const HostTriangle& tb = hs.tris[members[g][partner]];
+        ids.y = tb.idx;
+        push_edge(ta.edge[ja]);
+        push_edge(ta.edge[(ja + 1) % 3]); push_edge(ta.edge[(ja + 2) % 3]);
+        push_edge(tb.edge[(jb + 1) % 3]); push_edge(tb.edge[(jb + 2) % 3]);
+      } else {
+        ids.y = -1;
+        push_edge(ta.edge[0]); push_edge(ta.edge[1]); push_edge(ta.edge[2]);
+        push_edge(never); push_edge(never);
+      }
+      slot_ids->push_back(ids);
     }
-    if ((slot_tri->size() - (size_t)rg.x) & 1) {
-      // pad the group to an even number of slots with a triangle nothing can hit (edge offset +inf -> sd = +inf > 0),
-      // so the kernel's inner loop always handles two slots per trip without a remainder path
-      for (int j = 0; j < 3; j++) edges->push_back(make_float4(0.0f, 0.0f, 0.0f, INFINITY));
-      slot_tri->push_back(-1);
-    }
-    rg.y = (int)slot_tri->size();
+    rg.y = (int)slot_ids->size();
     grange->push_back(rg);
   }
 }
@@ -223,19 +249,18 @@ static int upload_scene(SceneHandle* h) {
   h->use_bvh = (g_traversal_mode == 2) || (g_traversal_mode == 0 && (int)nT > kBruteForceMaxTris);
   if (!h->use_bvh && nT) {
     std::vector<float4> planes, edges;
-    std::vector<int2> grange;
-    std::vector<int> slot_tri;
+    std::vector<int2> grange, slot_tri;
     build_plane_groups(hs, &planes, &grange, &edges, &slot_tri);
     h->n_groups = (int)planes.size();
     h->n_slots = (int)slot_tri.size();
     IPT_CUDA(cudaMalloc(&h->planes, planes.size() * sizeof(float4)));
     IPT_CUDA(cudaMalloc(&h->grange, grange.size() * sizeof(int2)));
     IPT_CUDA(cudaMalloc(&h->slot_edges, edges.size() * sizeof(float4)));
-    IPT_CUDA(cudaMalloc(&h->slot_tri, slot_tri.size() * sizeof(int)));
+    IPT_CUDA(cudaMalloc(&h->slot_tri, slot_tri.size() * sizeof(int2)));
     IPT_CUDA(cudaMemcpy(h->planes, planes.data(), planes.size() * sizeof(float4), cudaMemcpyHostToDevice));
     IPT_CUDA(cudaMemcpy(h->grange, grange.data(), grange.size() * sizeof(int2), cudaMemcpyHostToDevice));
     IPT_CUDA(cudaMemcpy(h->slot_edges, edges.data(), edges.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    IPT_CUDA(cudaMemcpy(h->slot_tri, slot_tri.data(), slot_tri.size() * sizeof(int), cudaMemcpyHostToDevice));
+    IPT_CUDA(cudaMemcpy(h->slot_tri, slot_tri.data(), slot_tri.size() * sizeof(int2), cudaMemcpyHostToDevice));
   }
   if (h->use_bvh && nT) {
     // triangle-level tree: box = vertex bounds, split position = triangle center (the analogue of

@@ -6,8 +6,8 @@
 //   plane groups (brute-force mode): triangles whose (n, k) are bit-identical share one plane test
 //     planes [G]    : {n.xyz, k}                 16 B / group
 //     grange [G]    : {first slot, end slot}      8 B / group
-//     slot_edges [3*nT] : {e.xyz, e.d} x 3       48 B / slot   (slots are grouped, ascending id inside a group)
-//     slot_tri [nT] : triangle id of the slot      4 B / slot
+//     slot_edges [5*nSlots] : {out.xyz, d} x 5   80 B / quad slot: shared diagonal, 2 edges of a, 2 edges of b
+//     slot_tri [nSlots] : triangle ids (a, b)      8 B / slot
 //   mat   [8*nT] : {Kd.rgb, Ns} {Ke.rgb, flags(bits)} {Kd/pi .rgb, 0} {n.xyz, 0} {Ks.rgb, area}
 //                  {R row0, 0} {R row1, 0} {R row2, 0}   (R = FromTwoVectors(z, n), path_trace.cu:102)   128 B / triangle
 //   light [3*nE] : {v0.xyz, cdf} {v1.xyz, p_t} {v2.xyz, tri index(bits)}             48 B / emissive
@@ -29,9 +29,9 @@ struct DevScene {
   const float4* planes;
   const int2* grange;
   const float4* slot_edges;
-  const int* slot_tri;
+  const int2* slot_tri;     // triangle ids (a, b) of each quad slot; b = -1 for an unpaired triangle
   int nGroups;
-  int nSlots;             // >= nT: groups are padded to an even slot count
+  int nSlots;             // quad slots (five edge records each)
   const float4* mat;
   const float4* light;
   const float4* vtx;
