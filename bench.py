@@ -334,7 +334,7 @@ def b200_arm(args):
         i1.record()
         barrier()
         ims = max_over_ranks(i0.elapsed_time(i1))
-        extra["inverse_scene0_500x500_64spp"] = {"iters_per_s": iters / (ims * 1e-3), "ms_per_iter": ims / iters, "loss_after": float(last)}
+        extra["inverse_scene0_500x500_64spp"] = {"iters_per_s": iters / (ims * 1e-3), "ms_per_iter": ims / iters, "loss_after": float(last.detach())}
         inv.close()
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -------------------------------------

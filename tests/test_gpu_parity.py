@@ -246,3 +246,69 @@ def test_gpu_bvh_builder_degenerate_and_scene_inputs(ipt, oracle):
         boxes = np.concatenate([pos - 0.01, pos + 0.02], 1).astype(np.float32) if pos is not t["center"] else np.concatenate([t["verts"].min(1), t["verts"].max(1)], 1)
         a, b = native.build_bvh(boxes, pos, builder=2), oracle.bvh_build(boxes, pos)
         assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1]) and a[0].tobytes() == b[0].tobytes()
+
+
+def test_torch_front_end_and_autograd(ipt, oracle):
+    """device-pointer entry points through torch tensors on torch's current stream; RenderLoss backward = path adjoint"""
+    import torch
+    from inverse_path_tracer_b200.torch_api import TorchScene, render_loss
+    objects = _scene0(oracle)
+    ts = TorchScene(objects, asset_root=ASSETS)
+    o = oracle.OracleScene(objects, ASSETS)
+    w, h, spp = 48, 40, 8
+    p = ipt.default_params(width=w, height=h, spp=spp, seed=21, max_depth=64)
+    img = ts.render(p)
+    ref, _ = o.render(oracle.make_params(w, h, spp, seed=21, max_depth=64))
+    assert img.cpu().numpy().tobytes() == ref.tobytes()
+    rng = np.random.RandomState(5)
+    target = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    kd0 = rng.uniform(0.2, 0.8, (ts.nT, 3)).astype(np.float32)
+    kd = torch.tensor(kd0, device="cuda", requires_grad=True)
+    loss = render_loss(kd, ts, p, torch.from_numpy(target).cuda())
+    loss.backward()
+    o.set_materials(kd0)
+    loss_o, grad_o, _ = o.render_grad(oracle.make_params(w, h, spp, seed=21, max_depth=64), target)
+    assert abs(float(loss.detach()) - loss_o) <= 1e-6 * abs(loss_o)
+    assert np.abs(kd.grad.cpu().numpy() - grad_o).max() <= 1e-3 * np.abs(grad_o).max()
+    # ray batches on the device + raw edge sums on the device
+    rays = torch.from_numpy(random_rays(100000, 3)).cuda()
+    tri, t = ts.trace(rays)
+    tri_o, t_o = o.trace(rays.cpu().numpy())
+    assert np.array_equal(tri.cpu().numpy(), tri_o) and t.cpu().numpy().tobytes() == t_o.tobytes()
+    raw = ts.graph_raw(p, torch.from_numpy(target).cuda()).cpu().numpy()
+    raw_o, _, _ = o.create_graph(oracle.make_params(w, h, spp, seed=21, max_depth=64), target)
+    np.testing.assert_allclose(raw, raw_o, rtol=2e-4, atol=1e-6)
+
+
+def test_full_size_properties(ipt, oracle):
+    """BASELINE config[1] resolution (1024 x 1024, depth 8) at reduced spp: properties that do not need the oracle --
+    one path per pixel-sample, run-to-run determinism, row shards reassemble the image bit for bit, different
+    sample grouping only reorders a float sum, and the image is statistically the golden Cornell box"""
+    g = ipt.Scene(scene_objects("cornell"), asset_root=ASSETS)
+    W = H = 1024
+    spp = 32
+    p = ipt.default_params(width=W, height=H, spp=spp, max_depth=8, seed=77)
+    a, ca = g.render(p)
+    b, cb = g.render(p)
+    assert ca == cb and ca["paths"] == W * H * spp
+    assert ca["ext_rays"] <= 8 * ca["paths"] and ca["shadow_rays"] <= ca["ext_rays"]
+    assert a.tobytes() == b.tobytes()
+    parts = [g.render(ipt.default_params(width=W, height=H, spp=spp, max_depth=8, seed=77, row_begin=rb, row_end=re))[0]
+             for rb, re in ((0, 128), (128, 129), (129, 700), (700, 1024))]
+    assert np.concatenate(parts, 0).tobytes() == a.tobytes()
+    c, _ = g.render(ipt.default_params(width=W, height=H, spp=spp, max_depth=8, seed=77, group_samples=5))
+    assert np.allclose(a, c, rtol=1e-5, atol=1e-6) and not np.array_equal(a, c)
+    assert np.isfinite(a).all() and (a >= 0).all()
+    light = a[215:270, 460:560].mean()       # the light quad seen from the eye: L_e = 10 re-added per bounce (quirk F5)
+    assert 14.0 < light < 19.0, light
+
+
+def test_scene_sharded_batch_smoke(ipt, oracle):
+    """BASELINE config 4 in miniature: independent scenes with their own handles render independently"""
+    scenes = [ipt.Scene(oracle.parse_scene_file(os.path.join(ASSETS, "scenes", "%d.txt" % i)), asset_root=ASSETS) for i in (3, 4, 5)]
+    p = ipt.default_params(width=64, height=64, spp=8, seed=1)
+    imgs = [s.render(p)[0] for s in scenes]
+    for i, s in zip((3, 4, 5), scenes):
+        o = oracle.OracleScene.from_file(os.path.join(ASSETS, "scenes", "%d.txt" % i), ASSETS)
+        assert imgs[(3, 4, 5).index(i)].tobytes() == o.render(oracle.make_params(64, 64, 8, seed=1))[0].tobytes()
+    assert not np.array_equal(imgs[0], imgs[1])
