@@ -82,6 +82,11 @@ int iptTraceRays(void* scene, const float* rays, int n, int* tri, float* t);
 /* same on device memory, asynchronous on `stream` (a cudaStream_t) */
 int iptTraceRaysDevice(void* scene, const float* rays_dev, int n, int* tri_dev, float* t_dev, void* stream);
 
+/* instrumented BVH traversal (device memory): stats_dev[0] = child boxes fetched (32 B each), stats_dev[1] = leaf
+ * triangles tested (64 B each) -- the algorithmic bytes of the L2/HBM roofline.  BVH-mode scenes only. */
+int iptTraceRaysStatsDevice(void* scene, const float* rays_dev, int n, int* tri_dev, float* t_dev,
+                            unsigned long long* stats_dev, void* stream);
+
 /* forward render of the row shard.  img: rows*width*3 float radiance means (may be NULL);
  * img8: rows*width*3 tone-mapped bytes (may be NULL); counters[3] = paths, extension rays,
  * shadow rays (may be NULL).  Host buffers, synchronous. */

@@ -550,6 +550,19 @@ int iptTraceRaysDevice(void* scene, const float* rays_dev, int n, int* tri_dev, 
   return 0;
 }
 
+int iptTraceRaysStatsDevice(void* scene, const float* rays_dev, int n, int* tri_dev, float* t_dev, unsigned long long* stats_dev, void* stream) {
+  SceneHandle* h = checked_device(scene);
+  if (!h) return -1;
+  if (n <= 0 || !rays_dev || !tri_dev || !t_dev || !stats_dev) return fail("iptTraceRaysStatsDevice: bad arguments");
+  if (!h->use_bvh) return fail("iptTraceRaysStatsDevice: the scene is in brute-force mode (no BVH to instrument)");
+  IPT_CUDA(cudaSetDevice(h->device));
+  IPT_CUDA(cudaMemsetAsync(stats_dev, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+  const int grid = std::min((n + 255) / 256, h->sm_count * 8);
+  IPT_CUDA(launch_trace_rays_stats(h->dev(), rays_dev, n, tri_dev, t_dev, stats_dev, grid, (cudaStream_t)stream));
+  g_launches += 1;
+  return 0;
+}
+
 int iptTraceRays(void* scene, const float* rays, int n, int* tri, float* t) {
   SceneHandle* h = checked_device(scene);
   if (!h) return -1;

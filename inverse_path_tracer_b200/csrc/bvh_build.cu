@@ -36,12 +36,6 @@ namespace ipt {
 
 namespace {
 
-struct Segment {
-  int start, end;
-  int parent;      // index into the segment list of the previous level (-1 for the root)
-  int is_right;    // 0 = left child, 1 = right child
-};
-
 struct BuildNode {
   float lo[3], hi[3];
   int start, count;

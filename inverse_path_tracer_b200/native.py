@@ -31,7 +31,7 @@ EXPORTS = ["loadScene", "freeScene", "createImage", "createGraph", "getMaterials
            "iptSceneInfo", "iptGetTriangleTable", "iptGetCamera", "iptTraceRays", "iptTraceRaysDevice",
            "iptRender", "iptRenderDevice", "iptCreateImageEx", "iptCreateGraphEx", "iptGraphAccumulateDevice",
            "iptGraphCompress", "iptRenderGrad", "iptRenderGradDevice", "iptSetMaterialsDevice", "iptBuildBVH",
-           "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder"]
+           "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder", "iptTraceRaysStatsDevice"]
 
 
 def lib():
@@ -55,6 +55,7 @@ def lib():
         L.iptGetCamera.argtypes = [vp, vp]
         L.iptTraceRays.argtypes = [vp, vp, C.c_int, vp, vp]
         L.iptTraceRaysDevice.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+        L.iptTraceRaysStatsDevice.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp]
         L.iptRender.argtypes = [vp, vp, vp, vp, vp]
         L.iptRenderDevice.argtypes = [vp, vp, vp, vp, vp, vp]
         L.iptCreateImageEx.argtypes = [vp, vp, C.c_char_p]

@@ -127,12 +127,20 @@ def main():
     rd = torch.from_numpy(rays).cuda()
     tri = torch.empty(n, dtype=torch.int32, device="cuda"); tt = torch.empty(n, dtype=torch.float32, device="cuda")
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    L.iptTraceRaysStatsDevice(sc.h, C.c_void_p(rd.data_ptr()), n, C.c_void_p(tri.data_ptr()), C.c_void_p(tt.data_ptr()), C.c_void_p(stats.data_ptr()), st)
+    torch.cuda.synchronize()
+    boxes_per_ray, tris_per_ray = float(stats[0]) / n, float(stats[1]) / n
+    bytes_per_ray = boxes_per_ray * 32 + tris_per_ray * 64
+    print("traversal work per incoherent ray: %.1f child boxes (32 B) + %.2f leaf triangles (64 B) = %.0f algorithmic bytes" % (boxes_per_ray, tris_per_ray, bytes_per_ray))
     for rep in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         L.iptTraceRaysDevice(sc.h, C.c_void_p(rd.data_ptr()), n, C.c_void_p(tri.data_ptr()), C.c_void_p(tt.data_ptr()), st)
         e1.record(); torch.cuda.synchronize()
-        print("incoherent closest hit: %d rays in %.2f ms -> %.1f Mrays/s (hit rate %.3f)" % (n, e0.elapsed_time(e1), n / e0.elapsed_time(e1) / 1e3, float((tri >= 0).float().mean())))
+        ms = e0.elapsed_time(e1)
+        print("incoherent closest hit: %d rays in %.2f ms -> %.1f Mrays/s (hit rate %.3f); %.0f GB/s of algorithmic node+triangle traffic (HBM copy peak 6555 GB/s)" % (
+            n, ms, n / ms / 1e3, float((tri >= 0).float().mean()), n * bytes_per_ray / ms / 1e6))
 
 
 if __name__ == "__main__":
