@@ -544,7 +544,7 @@ int iptTraceRaysDevice(void* scene, const float* rays_dev, int n, int* tri_dev, 
   if (n < 0 || (n > 0 && (!rays_dev || !tri_dev || !t_dev))) return fail("iptTraceRaysDevice: bad arguments");
   if (n == 0) return 0;
   IPT_CUDA(cudaSetDevice(h->device));
-  const int grid = std::min((n + 255) / 256, h->sm_count * 8);
+  const int grid = std::min((n + 127) / 128, h->sm_count * 16);
   IPT_CUDA(launch_trace_rays(h->dev(), rays_dev, n, tri_dev, t_dev, grid, (cudaStream_t)stream));
   g_launches += 1;
   return 0;
@@ -557,7 +557,7 @@ int iptTraceRaysStatsDevice(void* scene, const float* rays_dev, int n, int* tri_
   if (!h->use_bvh) return fail("iptTraceRaysStatsDevice: the scene is in brute-force mode (no BVH to instrument)");
   IPT_CUDA(cudaSetDevice(h->device));
   IPT_CUDA(cudaMemsetAsync(stats_dev, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
-  const int grid = std::min((n + 255) / 256, h->sm_count * 8);
+  const int grid = std::min((n + 127) / 128, h->sm_count * 16);
   IPT_CUDA(launch_trace_rays_stats(h->dev(), rays_dev, n, tri_dev, t_dev, stats_dev, grid, (cudaStream_t)stream));
   g_launches += 1;
   return 0;
