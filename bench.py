@@ -8,7 +8,7 @@
 
 Workload (BASELINE.json configs[1]): CornellBox-Empty-CO forward path trace, 1024 x 1024, 1024 spp,
 max depth 8, Russian roulette .9, Philox seed = step index.  One step = one full render of the image.
-At N > 1 the pixel rows are sharded (contiguous blocks), the scene is replicated, and the row blocks are
+At N > 1 the pixel rows are sharded (interleaved: rank, rank+N, ...), the scene is replicated, and the rows are
 all-gathered over NCCL inside the timed region (strong scaling: the image is fixed).
 
 Numbers:
@@ -200,12 +200,12 @@ def b200_arm(args):
         w.update(width=256, height=256, spp=64, name=w["name"] + " [SMALL DEV RUN 256x256x64 -- not a bench number]")
     ts = TorchScene(CORNELL, asset_root=ASSETS, device=local)
     nT = ts.nT
-    rb, re = parallel.shard_rows(w["height"], rank, world)
-    rows = re - rb
+    rb, re, rstep = parallel.shard_rows_interleaved(w["height"], rank, world)   # rows rank, rank+N, ...: equal work per GPU
+    rows = len(range(rb, re, rstep))
 
     def params(seed, **kw):
         base = dict(width=w["width"], height=w["height"], spp=w["spp"], max_depth=w["max_depth"], p_rr=w["p_rr"],
-                    group_samples=w["group_samples"], row_begin=rb, row_end=re, seed=seed)
+                    group_samples=w["group_samples"], row_begin=rb, row_end=re, row_step=rstep, seed=seed)
         base.update(kw)
         return ipt.default_params(**base)
 
@@ -217,7 +217,7 @@ def b200_arm(args):
     def step(seed):
         ts.render(params(seed), out=out, counters=counters)
         total.add_(counters)
-        img = parallel.gather_rows(out, w["height"]) if world > 1 else out
+        img = parallel.gather_rows_interleaved(out, w["height"]) if world > 1 else out
         flush.zero_()
         return img
 
@@ -281,9 +281,9 @@ def b200_arm(args):
     extra = {"mpaths_per_s": paths / (ms * 1e-3) / 1e6, "rays_per_path": rays / max(paths, 1),
              "kernel_ms_mean": k_ms, "kernel_share_of_step": k_ms * args.steps / max(ms, 1e-9)}
     if not args.no_extras:
-        hb, he = parallel.shard_rows(512, rank, world)
-        hp = lambda s: ipt.default_params(width=512, height=512, spp=64, max_depth=0, seed=s, row_begin=hb, row_end=he)
-        hout = torch.empty((he - hb, 512, 3), dtype=torch.float32, device=dev)
+        hb, he, hs = parallel.shard_rows_interleaved(512, rank, world)
+        hp = lambda s: ipt.default_params(width=512, height=512, spp=64, max_depth=0, seed=s, row_begin=hb, row_end=he, row_step=hs)
+        hout = torch.empty((len(range(hb, he, hs)), 512, 3), dtype=torch.float32, device=dev)
         for i in range(3):
             ts.render(hp(100 + i), out=hout, counters=counters)
         barrier()
@@ -295,7 +295,7 @@ def b200_arm(args):
             ts.render(hp(i), out=hout, counters=counters)
             total.add_(counters)
             if world > 1:
-                parallel.gather_rows(hout, 512)
+                parallel.gather_rows_interleaved(hout, 512)
             flush.zero_()
         h1.record()
         barrier()
@@ -309,13 +309,13 @@ def b200_arm(args):
         inv = TorchScene(objs, asset_root=ASSETS, device=local)
         from PIL import Image
         target = torch.from_numpy(np.asarray(Image.open(os.path.join(ROOT, "tests", "golden", "golden_0_true.png")).convert("RGB")).copy()).to(dev)
-        ib, ie = parallel.shard_rows(500, rank, world)
+        ib, ie, istep = parallel.shard_rows_interleaved(500, rank, world)   # 500 rows: shards may differ by one row; only sums are exchanged
         kd_param = torch.full((inv.nT, 3), 0.5, device=dev, requires_grad=True)
         opt = torch.optim.Adam([kd_param], lr=0.02)
 
         def inv_iter(it):
             opt.zero_grad(set_to_none=True)
-            p = ipt.default_params(width=500, height=500, spp=64, max_depth=0, seed=it, row_begin=ib, row_end=ie)
+            p = ipt.default_params(width=500, height=500, spp=64, max_depth=0, seed=it, row_begin=ib, row_end=ie, row_step=istep)
             loss = render_loss(kd_param, inv, p, target)
             loss.backward()
             opt.step()
@@ -354,7 +354,7 @@ def b200_arm(args):
                 "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["name"], "scene": "CornellBox-Empty-CO (18 triangles, 2 emissive), scene replicated",
-                           "sharding": "contiguous pixel-row blocks, all-gather of the float image" if world > 1 else "single GPU",
+                           "sharding": "interleaved pixel rows (rank, rank+N, ...), all-gather of the float image" if world > 1 else "single GPU",
                            "rng": "Philox4x32-10 keyed (pixel, sample, bounce), seed = step index",
                            "l2": "flushed between iterations by a 256 MiB device write (inside the timed region)"},
                 "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",

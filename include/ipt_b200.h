@@ -58,6 +58,8 @@ typedef struct IptRenderParams {
   uint32_t seed_lo, seed_hi;   /* Philox key */
   int group_samples;      /* samples accumulated sequentially per partial sum (<= 0: spp) */
   int row_begin, row_end; /* pixel-row shard [begin, end); row_end <= 0 means height */
+  int row_step;           /* every row_step-th row of the shard, starting at row_begin (<= 1: every row).  Interleaved
+                           * shards (begin = rank, step = world) balance the load across GPUs; outputs are compact */
 } IptRenderParams;
 
 const char* iptGetLastError(void);

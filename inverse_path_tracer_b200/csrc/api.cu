@@ -332,9 +332,12 @@ static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan)
   rp.c_diff = (1.0f / 0.318309873f) / p->p_rr;   // canon v2: diffuse coeff = cos * ((1 / (1/pi)) / p_rr), path_trace.cu:137
   rp.group_samples = (p->group_samples <= 0 || p->group_samples > p->spp) ? p->spp : p->group_samples;
   rp.groups = (p->spp + rp.group_samples - 1) / rp.group_samples;
-  rp.pix_begin = rb * p->width;
-  rp.n_pix = (re - rb) * p->width;
-  plan->rows = re - rb;
+  const int step = p->row_step < 1 ? 1 : p->row_step;
+  const int rows = (re - rb + step - 1) / step;
+  rp.row_begin = rb;
+  rp.row_step = step;
+  rp.n_pix = rows * p->width;
+  plan->rows = rows;
   return 0;
 }
 
@@ -353,7 +356,7 @@ static int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsi
   out.counters = counters_dev ? counters_dev : ctr;
   out.partial = (float*)h->partial.ptr;
   const size_t smem = paths_smem_bytes(sc, 0);
-  const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, smem);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, h->use_bvh, smem);
   {
     const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
     IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
@@ -387,7 +390,7 @@ void iptDefaultParams(IptRenderParams* p) {
   p->p_rr = 0.9f;                                  // scene.h:11
   p->seed_lo = 0; p->seed_hi = 0;
   p->group_samples = 64;
-  p->row_begin = 0; p->row_end = 0;
+  p->row_begin = 0; p->row_end = 0; p->row_step = 1;
 }
 
 int iptSetAssetRoot(const char* root) { g_asset_root = root ? root : ""; return 0; }
@@ -616,6 +619,7 @@ int iptCreateImageEx(void* scene, const IptRenderParams* p, const char* png_path
   IptRenderParams q = *p;
   q.row_begin = 0;
   q.row_end = 0;
+  q.row_step = 1;
   std::vector<unsigned char> px((size_t)q.width * q.height * 3);
   if (iptRender(scene, &q, nullptr, px.data(), nullptr) != 0) return -1;
   std::string err;
@@ -660,7 +664,7 @@ int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsign
   size_t smem = paths_smem_bytes(sc, acc_floats);
   out.acc_in_smem = smem <= 160 * 1024 ? 1 : 0;
   if (!out.acc_in_smem) smem = paths_smem_bytes(sc, 0);
-  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAPH_ID, smem);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAPH_ID, h->use_bvh, smem);
   if (out.acc_in_smem) {
     IPT_CUDA(h->block_acc.reserve((size_t)grid * acc_floats * sizeof(float)));
     out.block_acc = (float*)h->block_acc.ptr;
@@ -778,7 +782,7 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
   IPT_CUDA(cudaMemsetAsync(lossgrad_dev, 0, (size_t)(1 + 3 * nT) * sizeof(double), st));
   IPT_CUDA(h->dldpx.reserve(n3 * sizeof(float)));
   const double inv_n = 1.0 / (3.0 * (double)rp.width * (double)rp.height);
-  IPT_CUDA(launch_loss_dldpx(img, target_dev, rp.pix_begin, rp.n_pix, inv_n, 1.0f / (float)rp.spp, (float*)h->dldpx.ptr, lossgrad_dev, st));
+  IPT_CUDA(launch_loss_dldpx(img, target_dev, rp.row_begin, rp.row_step, rp.width, rp.n_pix, inv_n, 1.0f / (float)rp.spp, (float*)h->dldpx.ptr, lossgrad_dev, st));
   g_launches += 1;
   if (nT == 0) return 0;
   unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
@@ -793,7 +797,7 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
   size_t smem = paths_smem_bytes(sc, 3 * nT);
   out.acc_in_smem = smem <= 96 * 1024 ? 1 : 0;
   if (!out.acc_in_smem) smem = paths_smem_bytes(sc, 0);
-  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, smem);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, h->use_bvh, smem);
   if (out.acc_in_smem) {
     IPT_CUDA(h->block_acc.reserve((size_t)grid * 3 * nT * sizeof(float)));
     out.block_acc = (float*)h->block_acc.ptr;

@@ -51,8 +51,9 @@ struct DevRender {
   uint32_t key0, key1;
   int group_samples;    // samples per work item
   int groups;           // work items per pixel
-  int pix_begin;        // first global pixel index of this shard
-  int n_pix;            // pixels in this shard
+  int row_begin;        // first image row of this shard
+  int row_step;         // the shard owns rows row_begin, row_begin + row_step, ... (interleaved sharding)
+  int n_pix;            // pixels in this shard (compact local index = local_row * width + column)
 };
 
 // counters[0..2] = paths, extension rays, shadow rays

@@ -16,7 +16,7 @@ _LIB_PATH = os.environ.get("IPT_B200_LIB") or os.path.join(PKG, "lib", "libipt_b
 class IptRenderParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("spp", C.c_int), ("max_depth", C.c_int),
                 ("p_rr", C.c_float), ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32),
-                ("group_samples", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int)]
+                ("group_samples", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("row_step", C.c_int)]
 
 
 def library_path():
@@ -207,7 +207,8 @@ class Scene:
     @staticmethod
     def _rows(p):
         re = p.row_end if 0 < p.row_end <= p.height else p.height
-        return re - max(p.row_begin, 0)
+        step = max(p.row_step, 1)
+        return (re - max(p.row_begin, 0) + step - 1) // step
 
     def render(self, p, want_u8=False, img=None, img8=None):
         rows = self._rows(p)

@@ -799,6 +799,7 @@ struct Params {
   uint32_t seed_lo, seed_hi;
   int group_samples;                   // samples summed sequentially per partial (<=0: spp)
   int row_begin, row_end;              // rows rendered [begin,end) (pixel-row sharding)
+  int row_step;                        // every row_step-th row of that range (interleaved shards)
 };
 
 struct Counters {
@@ -1026,12 +1027,12 @@ static void render_pixel(const Scene& sc, const Params& P, int r, int c, float o
 }
 
 template <class F>
-static void parallel_rows(int r0, int r1, int threads, F fn) {
-  if (threads <= 1) { for (int r = r0; r < r1; r++) fn(r, 0); return; }
+static void parallel_rows(int r0, int r1, int threads, F fn, int step = 1) {
+  if (threads <= 1) { for (int r = r0; r < r1; r += step) fn(r, 0); return; }
   std::atomic<int> next(r0);
   std::vector<std::thread> pool;
   for (int t = 0; t < threads; t++)
-    pool.emplace_back([&, t]() { for (;;) { int r = next.fetch_add(1); if (r >= r1) break; fn(r, t); } });
+    pool.emplace_back([&, t]() { for (;;) { int r = next.fetch_add(step); if (r >= r1) break; fn(r, t); } });
   for (auto& th : pool) th.join();
 }
 
@@ -1152,6 +1153,7 @@ struct OrcParams {
   uint32_t seed_lo, seed_hi;
   int group_samples;
   int row_begin, row_end;
+  int row_step;
 };
 static Params to_params(const OrcParams* p) {
   Params P;
@@ -1160,6 +1162,7 @@ static Params to_params(const OrcParams* p) {
   P.row_begin = p->row_begin; P.row_end = p->row_end;
   if (P.row_end <= 0 || P.row_end > P.height) P.row_end = P.height;
   if (P.row_begin < 0) P.row_begin = 0;
+  P.row_step = p->row_step < 1 ? 1 : p->row_step;
   return P;
 }
 
@@ -1225,10 +1228,10 @@ void orc_render(void* h, const OrcParams* p, float* img, uint8_t* img8, uint64_t
     for (int c = 0; c < P.width; c++) {
       float px[3];
       render_pixel(*sc, P, r, c, px, &cnt[tid]);
-      size_t o = ((size_t)(r - P.row_begin) * P.width + c) * 3;
+      size_t o = ((size_t)((r - P.row_begin) / P.row_step) * P.width + c) * 3;
       for (int i = 0; i < 3; i++) { if (img) img[o + i] = px[i]; if (img8) img8[o + i] = tonemap_u8(px[i]); }
     }
-  });
+  }, P.row_step);
   if (counters) {
     counters[0] = counters[1] = counters[2] = 0;
     for (auto& c : cnt) { counters[0] += c.paths; counters[1] += c.ext_rays; counters[2] += c.shadow_rays; }
@@ -1263,7 +1266,7 @@ void orc_create_graph(void* h, const OrcParams* p, const uint8_t* target, double
       float pixel[3] = {(float)target[o] / 255.0f, (float)target[o + 1] / 255.0f, (float)target[o + 2] / 255.0f};  // inv_scene.h:74-77
       for (int s = 0; s < P.spp; s++) graph_sample(*sc, P, r, c, s, pixel, part[tid], &cnt[tid]);
     }
-  });
+  }, P.row_step);
   std::vector<Edge>& edges = part[0];
   for (int t = 1; t < threads; t++) for (size_t e = 0; e < nEdges; e++) edges[e].merge(part[t][e]);
   if (raw) {
@@ -1302,7 +1305,7 @@ void orc_render_grad(void* h, const OrcParams* p, const uint8_t* target, double*
       float px[3];
       render_pixel(*sc, P, r, c, px, &cnt);
       size_t o = ((size_t)r * P.width + c) * 3;
-      if (img) for (int i = 0; i < 3; i++) img[((size_t)(r - P.row_begin) * P.width + c) * 3 + i] = px[i];
+      if (img) for (int i = 0; i < 3; i++) img[((size_t)((r - P.row_begin) / P.row_step) * P.width + c) * 3 + i] = px[i];
       double dLdpx[3];
       for (int i = 0; i < 3; i++) {
         double L = px[i], y = L / (1.0 + L), ys = (double)target[o + i] / 255.0;
@@ -1349,7 +1352,7 @@ void orc_render_grad(void* h, const OrcParams* p, const uint8_t* target, double*
         }
       }
     }
-  });
+  }, P.row_step);
   double loss = 0.0;
   for (int t = 0; t < threads; t++) loss += lpart[t];
   *loss_out = loss;

@@ -17,13 +17,19 @@ REF_DUMP = os.path.join(HERE, "_ref", "ref_loader_dump")
 class OrcParams(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("spp", C.c_int), ("max_depth", C.c_int),
                 ("p_rr", C.c_float), ("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32),
-                ("group_samples", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int)]
+                ("group_samples", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("row_step", C.c_int)]
 
 
 def make_params(width=500, height=500, spp=100, max_depth=0, p_rr=0.9, seed=0, group_samples=64,
-                row_begin=0, row_end=0):
+                row_begin=0, row_end=0, row_step=1):
     return OrcParams(width, height, spp, max_depth, p_rr, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF,
-                     group_samples, row_begin, row_end)
+                     group_samples, row_begin, row_end, row_step)
+
+
+def n_rows(params):
+    re = params.row_end if 0 < params.row_end <= params.height else params.height
+    step = max(params.row_step, 1)
+    return (re - max(params.row_begin, 0) + step - 1) // step
 
 
 def build(force=False):
@@ -148,7 +154,7 @@ class OracleScene:
         return tri, t
 
     def render(self, params, threads=8, want_u8=False):
-        rows = (params.row_end if params.row_end > 0 else params.height) - params.row_begin
+        rows = n_rows(params)
         img = np.zeros((rows, params.width, 3), np.float32)
         img8 = np.zeros((rows, params.width, 3), np.uint8) if want_u8 else None
         cnt = np.zeros(3, np.uint64)
@@ -177,7 +183,7 @@ class OracleScene:
         assert target.shape == (params.height, params.width, 3)
         loss = C.c_double(0)
         grad = np.zeros((self.nT, 3), np.float64)
-        rows = (params.row_end if params.row_end > 0 else params.height) - params.row_begin
+        rows = n_rows(params)
         img = np.zeros((rows, params.width, 3), np.float32)
         lib().orc_render_grad(C.c_void_p(self.h), C.byref(params), _ptr(target), C.byref(loss), _ptr(grad), _ptr(img), threads)
         return loss.value, grad, img

@@ -32,6 +32,12 @@ def _worker(rank, world, port, tmpdir):
             return torch.from_numpy(img)
 
         full = parallel.render_sharded(render_rows, H)
+        # interleaved shards (what bench.py uses): H2 rows, H2 % world == 0
+        H2 = 18
+        b2, e2, s2 = parallel.shard_rows_interleaved(H2, rank, world)
+        part, _ = sc.render(O.make_params(W, H2, SPP, seed=5, max_depth=6, row_begin=b2, row_end=e2, row_step=s2), threads=2)
+        inter = parallel.gather_rows_interleaved(torch.from_numpy(part), H2)
+        np.save(os.path.join(tmpdir, "inter_%d.npy" % rank), inter.numpy())
         target = np.random.RandomState(3).randint(0, 256, (H, W, 3)).astype(np.uint8)
         b, e = parallel.shard_rows(H, rank, world)
         loss, grad, _ = sc.render_grad(O.make_params(W, H, SPP, seed=5, max_depth=6, row_begin=b, row_end=e), target, threads=2)
@@ -64,7 +70,9 @@ def test_two_rank_gloo_sharded_render_and_gradient(tmp_path, oracle):
     ref, _ = sc.render(oracle.make_params(W, H, SPP, seed=5, max_depth=6), threads=2)
     target = np.random.RandomState(3).randint(0, 256, (H, W, 3)).astype(np.uint8)
     loss, grad, _ = sc.render_grad(oracle.make_params(W, H, SPP, seed=5, max_depth=6), target, threads=2)
+    ref2, _ = sc.render(oracle.make_params(W, 18, SPP, seed=5, max_depth=6), threads=2)
     for r in range(world):
+        assert np.load(os.path.join(str(tmp_path), "inter_%d.npy" % r)).tobytes() == ref2.tobytes()
         img = np.load(os.path.join(str(tmp_path), "img_%d.npy" % r))
         assert img.shape == (H, W, 3) and img.tobytes() == ref.tobytes()          # bit-identical for any world size
         lg = np.load(os.path.join(str(tmp_path), "lg_%d.npy" % r))

@@ -122,6 +122,12 @@ def test_row_sharding_and_determinism(ipt, oracle):
         q = ipt.default_params(width=96, height=80, spp=32, seed=3, row_begin=rb, row_end=re)
         parts.append(g.render(q)[0])
     assert np.concatenate(parts, 0).tobytes() == full.tobytes()
+    # interleaved shards (rows r, r+3, ...): what bench.py uses at N > 1 for load balance
+    inter = np.empty_like(full)
+    for r0 in range(3):
+        q = ipt.default_params(width=96, height=80, spp=32, seed=3, row_begin=r0, row_end=80, row_step=3)
+        inter[r0::3] = g.render(q)[0]
+    assert inter.tobytes() == full.tobytes()
 
 
 def test_golden_image_statistics(ipt, oracle):
@@ -174,6 +180,13 @@ def test_grad_parity_and_finite_differences(ipt, oracle):
     loss_g, grad_g, img_g = g.render_grad(pg, target)
     loss_o, grad_o, img_o = o.render_grad(po, target)
     assert img_g.tobytes() == img_o.tobytes()
+    # interleaved row shards add up to the whole-image loss and gradient (the all-reduce of the inverse pass)
+    ls, gs = 0.0, np.zeros_like(grad_g)
+    for r0 in range(2):
+        l_, g_, _ = g.render_grad(ipt.default_params(width=w, height=h, spp=spp, seed=5, max_depth=64, row_begin=r0, row_end=h, row_step=2), target)
+        ls += l_
+        gs += g_
+    assert abs(ls - loss_g) <= 1e-9 * abs(loss_g) and np.abs(gs - grad_g).max() <= 1e-5 * np.abs(grad_g).max()
     assert abs(loss_g - loss_o) <= 1e-9 * abs(loss_o)
     scale = np.abs(grad_o).max()
     assert np.abs(grad_g - grad_o).max() <= 1e-3 * scale
