@@ -77,6 +77,9 @@ struct SceneHandle {
   float4* light = nullptr;
   float4* vtx = nullptr;
   float4* bvh_nodes = nullptr;
+  float4* bvh_wide = nullptr;
+  int bvh_root_desc = 0;
+  int bvh_depth = 1;
   int* bvh_prims = nullptr;
   int n_nodes = 0;
   bool use_bvh = false;
@@ -91,7 +94,7 @@ struct SceneHandle {
 
   DevScene dev() const {
     DevScene d;
-    d.geom = geom; d.planes = planes; d.grange = grange; d.slot_edges = slot_edges; d.slot_tri = slot_tri; d.nGroups = n_groups; d.nSlots = n_slots; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_prims = bvh_prims;
+    d.geom = geom; d.planes = planes; d.grange = grange; d.slot_edges = slot_edges; d.slot_tri = slot_tri; d.nGroups = n_groups; d.nSlots = n_slots; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
     d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.use_bvh = use_bvh ? 1 : 0;
     memcpy(d.cam, host.cam, sizeof(d.cam));
     return d;
@@ -100,7 +103,7 @@ struct SceneHandle {
     if (host_only) return;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    cudaFree(geom); cudaFree(planes); cudaFree(grange); cudaFree(slot_edges); cudaFree(slot_tri); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_prims);
+    cudaFree(geom); cudaFree(planes); cudaFree(grange); cudaFree(slot_edges); cudaFree(slot_tri); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_wide); cudaFree(bvh_prims);
     Scratch* all[] = {&partial, &counters, &cnt_out, &block_acc, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
     for (Scratch* s : all) s->release();
     if (stream) cudaStreamDestroy(stream);
@@ -300,7 +303,33 @@ static int upload_scene(SceneHandle* h) {
       packed[2 * i] = make_float4(lo[0], lo[1], lo[2], a);
       packed[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], b);
     }
+    // traversal records: every inner node carries both (padded) child boxes and the child descriptors
+    auto desc_of = [&](size_t c) {
+      return nodes[c].rightOffset != 0 ? (int)c : ~((nodes[c].start << 3) | (nodes[c].nPrims & 7));
+    };
+    std::vector<float4> wide(4 * nodes.size(), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    std::vector<int> depth(nodes.size(), 1);
+    int max_depth = 1;
+    for (size_t i = 0; i < nodes.size(); i++) {
+      if (nodes[i].rightOffset == 0) continue;
+      const size_t l = i + 1, r = i + (size_t)nodes[i].rightOffset;
+      depth[l] = depth[r] = depth[i] + 1;                 // parents precede children in DFS pre-order
+      max_depth = std::max(max_depth, depth[i] + 1);
+      int dl = desc_of(l), dr = desc_of(r);
+      float fl, fr;
+      memcpy(&fl, &dl, 4);
+      memcpy(&fr, &dr, 4);
+      wide[4 * i + 0] = make_float4(packed[2 * l].x, packed[2 * l].y, packed[2 * l].z, fl);
+      wide[4 * i + 1] = make_float4(packed[2 * l + 1].x, packed[2 * l + 1].y, packed[2 * l + 1].z, fr);
+      wide[4 * i + 2] = make_float4(packed[2 * r].x, packed[2 * r].y, packed[2 * r].z, 0.0f);
+      wide[4 * i + 3] = make_float4(packed[2 * r + 1].x, packed[2 * r + 1].y, packed[2 * r + 1].z, 0.0f);
+    }
+    if (max_depth > 64) return fail("BVH deeper than 64 levels: the traversal stack (like the reference's todo[64], bvh.h:43) cannot hold it");
+    h->bvh_root_desc = desc_of(0);
+    h->bvh_depth = max_depth;
     h->n_nodes = (int)nodes.size();
+    IPT_CUDA(cudaMalloc(&h->bvh_wide, wide.size() * sizeof(float4)));
+    IPT_CUDA(cudaMemcpy(h->bvh_wide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice));
     IPT_CUDA(cudaMalloc(&h->bvh_nodes, packed.size() * sizeof(float4)));
     IPT_CUDA(cudaMalloc(&h->bvh_prims, perm.size() * sizeof(int)));
     IPT_CUDA(cudaMemcpy(h->bvh_nodes, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice));

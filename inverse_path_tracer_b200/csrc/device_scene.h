@@ -13,7 +13,8 @@
 //   light [3*nE] : {v0.xyz, cdf} {v1.xyz, p_t} {v2.xyz, tri index(bits)}             48 B / emissive
 //   vtx   [5*nT] : {v0.xyz, vn0.x} {v1.xyz, vn0.y} {v2.xyz, vn0.z} {vn1.xyz, area} {vn2.xyz, 0}
 //                  (only read for triangles that carry per-vertex normals: Triangle::getNormal)
-//   bvh nodes [2*nNodes] : {lo.xyz, start|rightOffset(bits)} {hi.xyz, nPrims(bits)}   32 B / node
+//   bvh nodes [2*nNodes] : {lo.xyz, rightOffset(bits)} {hi.xyz, start<<3|nPrims (bits)}   32 B / node (canonical DFS layout)
+//   bvh wide  [4*nNodes] : {L.lo, desc L} {L.hi, desc R} {R.lo, -} {R.hi, -}             64 B / inner node (traversal)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,7 +36,10 @@ struct DevScene {
   const float4* mat;
   const float4* light;
   const float4* vtx;
-  const float4* bvh_nodes;   // null in brute-force mode
+  const float4* bvh_nodes;   // null in brute-force mode; canonical 32-byte nodes (root box, layout parity)
+  const float4* bvh_wide;    // 64-byte traversal records: both child boxes + child descriptors per inner node
+  int bvh_root_desc;         // descriptor of the root (0 = inner node 0, negative = the root is a leaf)
+  int bvh_depth;             // levels of the tree = entries of the per-thread traversal stack (<= 64)
   const int* bvh_prims;      // triangle index per BVH slot
   int nT, nE, nNodes;
   int use_bvh;
