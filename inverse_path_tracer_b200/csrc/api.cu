@@ -89,7 +89,7 @@ struct SceneHandle {
   static constexpr int kEventRing = 64;
   cudaEvent_t ev_start[kEventRing] = {}, ev_stop[kEventRing] = {};
   unsigned long long ev_count = 0;   // loaded with iptSetDevice(-2): tables only, no device arrays
-  Scratch partial, counters, cnt_out, block_acc, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
+  Scratch partial, counters, cnt_out, trace_counter, block_acc, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
   std::mutex mutex;
 
   DevScene dev() const {
@@ -104,7 +104,7 @@ struct SceneHandle {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     cudaFree(geom); cudaFree(planes); cudaFree(grange); cudaFree(slot_edges); cudaFree(slot_tri); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_wide); cudaFree(bvh_prims);
-    Scratch* all[] = {&partial, &counters, &cnt_out, &block_acc, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
+    Scratch* all[] = {&partial, &counters, &cnt_out, &trace_counter, &block_acc, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
     for (Scratch* s : all) s->release();
     if (stream) cudaStreamDestroy(stream);
     for (int i = 0; i < kEventRing; i++) { if (ev_start[i]) cudaEventDestroy(ev_start[i]); if (ev_stop[i]) cudaEventDestroy(ev_stop[i]); }
@@ -576,8 +576,8 @@ int iptTraceRaysDevice(void* scene, const float* rays_dev, int n, int* tri_dev, 
   if (n < 0 || (n > 0 && (!rays_dev || !tri_dev || !t_dev))) return fail("iptTraceRaysDevice: bad arguments");
   if (n == 0) return 0;
   IPT_CUDA(cudaSetDevice(h->device));
-  const int grid = std::min((n + 127) / 128, h->sm_count * 16);
-  IPT_CUDA(launch_trace_rays(h->dev(), rays_dev, n, tri_dev, t_dev, grid, (cudaStream_t)stream));
+  IPT_CUDA(h->trace_counter.reserve(sizeof(unsigned long long)));
+  IPT_CUDA(launch_trace_rays(h->dev(), rays_dev, n, tri_dev, t_dev, (unsigned long long*)h->trace_counter.ptr, h->sm_count, (cudaStream_t)stream));
   g_launches += 1;
   return 0;
 }
@@ -589,8 +589,9 @@ int iptTraceRaysStatsDevice(void* scene, const float* rays_dev, int n, int* tri_
   if (!h->use_bvh) return fail("iptTraceRaysStatsDevice: the scene is in brute-force mode (no BVH to instrument)");
   IPT_CUDA(cudaSetDevice(h->device));
   IPT_CUDA(cudaMemsetAsync(stats_dev, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
-  const int grid = std::min((n + 127) / 128, h->sm_count * 16);
-  IPT_CUDA(launch_trace_rays_stats(h->dev(), rays_dev, n, tri_dev, t_dev, stats_dev, grid, (cudaStream_t)stream));
+  IPT_CUDA(h->trace_counter.reserve(sizeof(unsigned long long)));
+  IPT_CUDA(launch_trace_rays_stats(h->dev(), rays_dev, n, tri_dev, t_dev, (unsigned long long*)h->trace_counter.ptr, stats_dev, h->sm_count,
+                                   (cudaStream_t)stream));
   g_launches += 1;
   return 0;
 }

@@ -14,8 +14,9 @@ enum { MODE_RENDER_ID = 0, MODE_GRAPH_ID = 1, MODE_GRAD_ID = 2 };
 size_t paths_smem_bytes(const DevScene& sc, int acc_floats);
 int paths_blocks_per_sm(int mode, bool bvh, size_t smem);
 cudaError_t launch_paths(int mode, const DevScene& sc, const DevRender& rp, const DevOut& out, int grid, size_t smem, cudaStream_t st);
-cudaError_t launch_trace_rays(const DevScene& sc, const float* rays, int n, int* tri, float* t, int grid, cudaStream_t st);
-cudaError_t launch_trace_rays_stats(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* stats, int grid, cudaStream_t st);
+cudaError_t launch_trace_rays(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter, int sm_count, cudaStream_t st);
+cudaError_t launch_trace_rays_stats(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter,
+                                    unsigned long long* stats, int sm_count, cudaStream_t st);
 cudaError_t launch_resolve(const float* partial, int n_pix, int groups, float* img, unsigned char* img8, cudaStream_t st);
 cudaError_t launch_loss_dldpx(const float* img, const unsigned char* target, int row_begin, int row_step, int width, int n_pix, double inv_n, float inv_spp,
                               float* dldpx, double* loss, cudaStream_t st);
