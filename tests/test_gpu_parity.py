@@ -325,3 +325,45 @@ def test_scene_sharded_batch_smoke(ipt, oracle):
         o = oracle.OracleScene.from_file(os.path.join(ASSETS, "scenes", "%d.txt" % i), ASSETS)
         assert imgs[(3, 4, 5).index(i)].tobytes() == o.render(oracle.make_params(64, 64, 8, seed=1))[0].tobytes()
     assert not np.array_equal(imgs[0], imgs[1])
+
+
+def test_edge_case_scenes(ipt, oracle, tmp_path):
+    """empty scene, a scene without lights, a single triangle, and a one-pixel / one-sample image"""
+    p = ipt.default_params(width=16, height=12, spp=4, seed=3)
+    po = oracle.make_params(16, 12, 4, seed=3)
+    # no objects at all: every ray misses, the image is black, one extension ray per path
+    g = ipt.Scene([], asset_root=ASSETS)
+    assert g.nT == 0 and g.nE == 0
+    img, cnt = g.render(p)
+    assert not img.any() and cnt == {"paths": 16 * 12 * 4, "ext_rays": 16 * 12 * 4, "shadow_rays": 0}
+    tri, t = g.trace(random_rays(1000, 1))
+    assert (tri == -1).all() and np.isinf(t).all()
+    # geometry but no emitter (nE == 0): directLighting returns before drawing (path_trace.cu:33-34)
+    cube = [{"pos": [0, 0, 3], "ori": [0.3, 0.2, 0.1], "scl": [1, 1, 1], "obj": "./shapes/cube.obj", "mtl": "*Kd 0.5 0.6 0.7*"}]
+    g, o = _pair(ipt, oracle, cube)
+    assert g.nE == 0
+    ig, cg = g.render(p)
+    io, co = o.render(po)
+    assert cg == co and ig.tobytes() == io.tobytes() and not ig.any() and cg["shadow_rays"] == 0
+    raw_g, data_g, _ = g.create_graph(p, np.zeros((12, 16, 3), np.uint8))
+    raw_o, data_o, _ = o.create_graph(po, np.zeros((12, 16, 3), np.uint8))
+    assert np.array_equal(raw_g[:, 0], raw_o[:, 0]) and not np.isnan(data_g).any()
+    # one emissive triangle seen from the eye (an unpaired quad slot, a one-slot group)
+    obj = tmp_path / "tri.obj"
+    obj.write_text("mtllib t.mtl\nusemtl lamp\nv -1 -1 3\nv 1 -1 3\nv 0 1 3\nf 1 2 3\n")
+    (tmp_path / "t.mtl").write_text("newmtl lamp\nKd 0.5 0.5 0.5\nKe 3 2 1\n")
+    one = [{"pos": [0, 0, 0], "ori": [0, 0, 0], "scl": [1, 1, 1], "obj": str(obj), "mtl": str(tmp_path / "t.mtl")}]
+    g, o = _pair(ipt, oracle, one)
+    assert (g.nT, g.nE) == (1, 1)
+    ig, cg = g.render(p)
+    io, co = o.render(po)
+    assert cg == co and ig.tobytes() == io.tobytes() and ig.max() > 0
+    # 1 x 1 pixel, 1 sample
+    q, qo = ipt.default_params(width=1, height=1, spp=1, seed=9), oracle.make_params(1, 1, 1, seed=9)
+    g, o = _pair(ipt, oracle, scene_objects("cornell"))
+    assert g.render(q)[0].tobytes() == o.render(qo)[0].tobytes()
+    # bad parameters are reported, not executed
+    with pytest.raises(RuntimeError, match="positive"):
+        g.render(ipt.default_params(width=0, height=4, spp=1))
+    with pytest.raises(RuntimeError, match="empty row shard"):
+        g.render(ipt.default_params(width=4, height=4, spp=1, row_begin=4, row_end=4))
