@@ -95,7 +95,7 @@ struct SceneHandle {
   DevScene dev() const {
     DevScene d;
     d.geom = geom; d.planes = planes; d.grange = grange; d.slot_edges = slot_edges; d.slot_tri = slot_tri; d.nGroups = n_groups; d.nSlots = n_slots; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
-    d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.use_bvh = use_bvh ? 1 : 0;
+    d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.use_bvh = use_bvh ? 1 : 0; d.plain = (!host.any_vn && !host.any_specular) ? 1 : 0;
     memcpy(d.cam, host.cam, sizeof(d.cam));
     return d;
   }
@@ -385,7 +385,7 @@ static int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsi
   out.counters = counters_dev ? counters_dev : ctr;
   out.partial = (float*)h->partial.ptr;
   const size_t smem = paths_smem_bytes(sc, 0);
-  const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, h->use_bvh, smem);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, sc, smem);
   {
     const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
     IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
@@ -694,7 +694,7 @@ int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsign
   size_t smem = paths_smem_bytes(sc, acc_floats);
   out.acc_in_smem = smem <= 160 * 1024 ? 1 : 0;
   if (!out.acc_in_smem) smem = paths_smem_bytes(sc, 0);
-  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAPH_ID, h->use_bvh, smem);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAPH_ID, sc, smem);
   if (out.acc_in_smem) {
     IPT_CUDA(h->block_acc.reserve((size_t)grid * acc_floats * sizeof(float)));
     out.block_acc = (float*)h->block_acc.ptr;
@@ -827,7 +827,7 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
   size_t smem = paths_smem_bytes(sc, 3 * nT);
   out.acc_in_smem = smem <= 96 * 1024 ? 1 : 0;
   if (!out.acc_in_smem) smem = paths_smem_bytes(sc, 0);
-  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, h->use_bvh, smem);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, sc, smem);
   if (out.acc_in_smem) {
     IPT_CUDA(h->block_acc.reserve((size_t)grid * 3 * nT * sizeof(float)));
     out.block_acc = (float*)h->block_acc.ptr;

@@ -43,6 +43,7 @@ struct DevScene {
   const int* bvh_prims;      // triangle index per BVH slot
   int nT, nE, nNodes;
   int use_bvh;
+  int plain;                 // no per-vertex normals and no specular lobe anywhere in the scene
   float cam[16];
 };
 
