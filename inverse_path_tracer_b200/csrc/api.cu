@@ -348,6 +348,7 @@ static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan)
   if (!p) return fail("null render params");
   if (p->width <= 0 || p->height <= 0 || p->spp <= 0) return fail("width, height and spp must be positive");
   if (!(p->p_rr > 0.0f)) return fail("p_rr must be positive");
+  if (p->p_rr >= 1.0f && p->max_depth <= 0) return fail("unbounded depth needs p_rr < 1 (paths would never terminate in a closed scene)");
   int rb = p->row_begin < 0 ? 0 : p->row_begin;
   int re = (p->row_end <= 0 || p->row_end > p->height) ? p->height : p->row_end;
   if (rb >= re) return fail("empty row shard");
