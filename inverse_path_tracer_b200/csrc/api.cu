@@ -825,13 +825,19 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
   out.target = target_dev;
   out.dldpx = (const float*)h->dldpx.ptr;
   out.acc_stride = 3 * nT;
-  size_t smem = paths_smem_bytes(sc, 3 * nT);
-  out.acc_in_smem = smem <= 96 * 1024 ? 1 : 0;
-  if (!out.acc_in_smem) smem = paths_smem_bytes(sc, 0);
+  // gradient tiles: one [3 nT] float tile per block in global memory, updated with fire-and-forget float
+  // reductions (shared-memory float atomics are compare-and-swap loops on this architecture); scenes whose
+  // tiles would be too large fall back to double atomics on the result itself
+  const char* acc_env = getenv("IPT_GRAD_ACC");   // developer A/B: 0 = global double, 1 = shared tile, 2 = global tile
+  size_t smem = paths_smem_bytes(sc, 0);
+  out.acc_in_smem = (3 * (size_t)nT <= 65536) ? 2 : 0;
+  if (acc_env && *acc_env) out.acc_in_smem = atoi(acc_env);
+  if (out.acc_in_smem == 1) smem = paths_smem_bytes(sc, 3 * nT);
   const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, sc, smem);
   if (out.acc_in_smem) {
     IPT_CUDA(h->block_acc.reserve((size_t)grid * 3 * nT * sizeof(float)));
     out.block_acc = (float*)h->block_acc.ptr;
+    if (out.acc_in_smem == 2) IPT_CUDA(cudaMemsetAsync(out.block_acc, 0, (size_t)grid * 3 * nT * sizeof(float), st));
   } else {
     out.global_acc = lossgrad_dev + 1;
   }

@@ -71,7 +71,8 @@ struct DevOut {
   float* block_acc;          // [gridDim.x * acc_stride] per-block partial sums (graph / grad)
   double* global_acc;        // direct global accumulation when the scene does not fit shared memory
   int acc_stride;
-  int acc_in_smem;
+  int acc_in_smem;           // 0: double atomics on global_acc; 1: per-block tile in shared memory, flushed to block_acc;
+                             // 2: float reductions (RED.ADD.F32, no CAS loop) straight into this block's tile of block_acc
 };
 
 constexpr int kGraphAccPerEdge = 10;   // W_i, Wpix_i[3], W_d, Wpix_d[3], n_i, n_d
