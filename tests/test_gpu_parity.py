@@ -372,4 +372,4 @@ def test_edge_case_scenes(ipt, oracle, tmp_path):
     # p_rr = 1 is fine with a depth limit: every path runs to max_depth or leaves the scene
     a_, ca_ = g.render(ipt.default_params(width=8, height=8, spp=2, p_rr=1.0, max_depth=4, seed=2))
     b_, cb_ = o.render(oracle.make_params(8, 8, 2, p_rr=1.0, max_depth=4, seed=2))
-    assert ca_ == cb_ and a_.tobytes() == b_.tobytes() and ca_["ext_rays"] == 4 * ca_["paths"]
+    assert ca_ == cb_ and a_.tobytes() == b_.tobytes() and 3 * ca_["paths"] < ca_["ext_rays"] <= 4 * ca_["paths"]   # a few paths leave through the open front
