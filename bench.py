@@ -335,6 +335,36 @@ def b200_arm(args):
         barrier()
         ims = max_over_ranks(i0.elapsed_time(i1))
         extra["inverse_scene0_500x500_64spp"] = {"iters_per_s": iters / (ims * 1e-3), "ms_per_iter": ims / iters, "loss_after": float(last.detach())}
+        # ---- scene-sharded batch inverse (BASELINE config 4): every rank fits its own scene (scenes/<rank>.txt) against
+        #      its own target (forward render, 100 spp, seed = scene id); no collective; aggregate iterations/s
+        mine = TorchScene(parse_scene_file(os.path.join(ASSETS, "scenes", "%d.txt" % rank)), asset_root=ASSETS, device=local)
+        tgt8 = torch.empty((500, 500, 3), dtype=torch.uint8, device=dev)
+        mine.render(ipt.default_params(width=500, height=500, spp=100, seed=rank), out_u8=tgt8)
+        kd2 = torch.full((mine.nT, 3), 0.5, device=dev, requires_grad=True)
+        opt2 = torch.optim.Adam([kd2], lr=0.02)
+
+        def batch_iter(it):
+            opt2.zero_grad(set_to_none=True)
+            loss = render_loss(kd2, mine, ipt.default_params(width=500, height=500, spp=64, max_depth=0, seed=it), tgt8, reduce=False)
+            loss.backward()
+            opt2.step()
+            with torch.no_grad():
+                kd2.clamp_(1e-3, 1.0)
+            return loss
+
+        for it in range(3):
+            batch_iter(1000 + it)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for it in range(iters):
+            lastb = batch_iter(it)
+        b1.record()
+        barrier()
+        bms = max_over_ranks(b0.elapsed_time(b1))
+        extra["inverse_batch_scene_sharded_500x500_64spp"] = {"iters_per_s": world * iters / (bms * 1e-3), "scenes_in_flight": world,
+                                                               "ms_per_iter_per_gpu": bms / iters, "loss_after_rank0": float(lastb.detach())}
+        mine.close()
         inv.close()
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -------------------------------------

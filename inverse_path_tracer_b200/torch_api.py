@@ -96,10 +96,10 @@ class RenderLoss(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, kd, tscene, params, target_u8, group=None):
+    def forward(ctx, kd, tscene, params, target_u8, group=None, reduce=True):
         tscene.set_materials(kd)
         lg = tscene.loss_and_grad(params, target_u8)
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        if reduce and (group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
             torch.distributed.all_reduce(lg, group=group)
         ctx.save_for_backward(lg[1:].view(-1, 3).to(kd.dtype))
         return lg[0].to(kd.dtype)
@@ -107,8 +107,10 @@ class RenderLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         (g,) = ctx.saved_tensors
-        return grad_out * g, None, None, None, None
+        return grad_out * g, None, None, None, None, None
 
 
-def render_loss(kd, tscene, params, target_u8, group=None):
-    return RenderLoss.apply(kd, tscene, params, target_u8, group)
+def render_loss(kd, tscene, params, target_u8, group=None, reduce=True):
+    """reduce=True: `params` describes this rank's row shard of ONE scene, loss and gradient are summed over the
+    ranks of `group`.  reduce=False: the scene belongs to this rank alone (scene-sharded batches, BASELINE config 4)."""
+    return RenderLoss.apply(kd, tscene, params, target_u8, group, reduce)
