@@ -89,7 +89,7 @@ struct SceneHandle {
   static constexpr int kEventRing = 64;
   cudaEvent_t ev_start[kEventRing] = {}, ev_stop[kEventRing] = {};
   unsigned long long ev_count = 0;   // loaded with iptSetDevice(-2): tables only, no device arrays
-  Scratch partial, counters, cnt_out, trace_counter, block_acc, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
+  Scratch partial, counters, cnt_out, trace_counter, block_acc, vstacks, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
   std::mutex mutex;
 
   DevScene dev() const {
@@ -104,7 +104,7 @@ struct SceneHandle {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     cudaFree(geom); cudaFree(planes); cudaFree(grange); cudaFree(slot_edges); cudaFree(slot_tri); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_wide); cudaFree(bvh_prims);
-    Scratch* all[] = {&partial, &counters, &cnt_out, &trace_counter, &block_acc, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
+    Scratch* all[] = {&partial, &counters, &cnt_out, &trace_counter, &block_acc, &vstacks, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
     for (Scratch* s : all) s->release();
     if (stream) cudaStreamDestroy(stream);
     for (int i = 0; i < kEventRing; i++) { if (ev_start[i]) cudaEventDestroy(ev_start[i]); if (ev_stop[i]) cudaEventDestroy(ev_stop[i]); }
@@ -848,6 +848,11 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
   } else {
     out.global_acc = lossgrad_dev + 1;
   }
+  // adjoint vertex stacks: two halves of max_depth 32-byte vertices per resident thread (no initialisation needed:
+  // a sweep only reads what its own path wrote)
+  out.vdepth = q.max_depth;
+  IPT_CUDA(h->vstacks.reserve((size_t)grid * paths_block_threads() * 2 * (size_t)out.vdepth * 32));
+  out.vstacks = (float4*)h->vstacks.ptr;
   {
     const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
     IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));

@@ -70,6 +70,8 @@ struct DevOut {
   const float* dldpx;        // [n_pix * 3] dLoss/dL_pixel / spp  (grad)
   float* block_acc;          // [gridDim.x * acc_stride] per-block partial sums (graph / grad)
   double* global_acc;        // direct global accumulation when the scene does not fit shared memory
+  float4* vstacks;           // adjoint vertex stacks: per warp [2 halves][vdepth][32 lanes] x 32-byte vertices (grad)
+  int vdepth;                // vertices per stack half (= clamped max_depth)
   int acc_stride;
   int acc_in_smem;           // 0: double atomics on global_acc; 1: per-block tile in shared memory, flushed to block_acc;
                              // 2: float reductions (RED.ADD.F32, no CAS loop) straight into this block's tile of block_acc

@@ -13,6 +13,7 @@ enum { MODE_RENDER_ID = 0, MODE_GRAPH_ID = 1, MODE_GRAD_ID = 2 };
 
 size_t paths_smem_bytes(const DevScene& sc, int acc_floats);
 int paths_blocks_per_sm(int mode, const DevScene& sc, size_t smem);
+int paths_block_threads();   // threads per block of k_paths
 cudaError_t launch_paths(int mode, const DevScene& sc, const DevRender& rp, const DevOut& out, int grid, size_t smem, cudaStream_t st);
 cudaError_t launch_trace_rays(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter, int sm_count, cudaStream_t st);
 cudaError_t launch_trace_rays_stats(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter,
