@@ -127,6 +127,12 @@ int iptBuildBVH(const float* boxes, const float* pos, int n, int leaf_size, floa
  * on, one host thread below), 1 = host, 2 = CUDA kernels.  All produce bit-identical trees. */
 int iptSetBvhBuilder(int mode);
 
+/* forward integrator for scenes traversed through the BVH: 0 = auto (wavefront), 1 = persistent megakernel
+ * (the one brute-force scenes always use), 2 = wavefront: path state in device memory, one closest-hit
+ * kernel per bounce over the compacted live paths.  `wavefront_slots` bounds the paths in flight per batch
+ * (0 = default, 16 Mi).  All produce bit-identical images.  Applies to later render calls. */
+int iptSetIntegrator(int mode, int wavefront_slots);
+
 int iptWritePNG(const char* path, const unsigned char* rgb, int width, int height);
 int iptReadPNG(const char* path, unsigned char* rgb, int capacity_bytes, int* width, int* height);
 

@@ -30,6 +30,8 @@ static thread_local std::string g_error;
 static std::string g_asset_root;
 static thread_local int g_device = -1;
 static int g_traversal_mode = 0;
+static int g_integrator = 0;          // 0 auto, 1 megakernel, 2 wavefront (BVH scenes)
+static int g_wf_slots = 1 << 24;
 static std::atomic<unsigned long long> g_launches(0);
 static std::mutex g_registry_mutex;
 static std::set<void*> g_registry;
@@ -89,6 +91,8 @@ struct SceneHandle {
   static constexpr int kEventRing = 64;
   cudaEvent_t ev_start[kEventRing] = {}, ev_stop[kEventRing] = {};
   unsigned long long ev_count = 0;   // loaded with iptSetDevice(-2): tables only, no device arrays
+  int* host_live = nullptr;          // pinned word for the wavefront integrator's live count
+  Scratch wavefront;
   Scratch partial, counters, cnt_out, trace_counter, block_acc, vstacks, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
   std::mutex mutex;
 
@@ -104,8 +108,9 @@ struct SceneHandle {
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
     cudaFree(geom); cudaFree(planes); cudaFree(grange); cudaFree(slot_edges); cudaFree(slot_tri); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_wide); cudaFree(bvh_prims);
-    Scratch* all[] = {&partial, &counters, &cnt_out, &trace_counter, &block_acc, &vstacks, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
+    Scratch* all[] = {&wavefront, &partial, &counters, &cnt_out, &trace_counter, &block_acc, &vstacks, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
     for (Scratch* s : all) s->release();
+    if (host_live) cudaFreeHost(host_live);
     if (stream) cudaStreamDestroy(stream);
     for (int i = 0; i < kEventRing; i++) { if (ev_start[i]) cudaEventDestroy(ev_start[i]); if (ev_stop[i]) cudaEventDestroy(ev_stop[i]); }
   }
@@ -385,17 +390,31 @@ static int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsi
   out.work_counter = ctr + 4;
   out.counters = counters_dev ? counters_dev : ctr;
   out.partial = (float*)h->partial.ptr;
-  const size_t smem = paths_smem_bytes(sc, 0);
-  const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, sc, smem);
-  {
+  if (sc.use_bvh && g_integrator != 1) {
+    // large scenes: wavefront (kernels.cu); batches of at most `cap` paths
+    const long long total = (long long)rp.n_pix * std::min(rp.spp, rp.group_samples);
+    const int cap = (int)std::max<long long>(1, std::min<long long>(total, (long long)g_wf_slots));
+    IPT_CUDA(h->wavefront.reserve(wavefront_workspace_bytes(cap)));
+    if (!h->host_live) IPT_CUDA(cudaHostAlloc((void**)&h->host_live, sizeof(int), cudaHostAllocDefault));
+    const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
+    IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
+    unsigned long long launches = 0;
+    IPT_CUDA(launch_wavefront(sc, rp, h->wavefront.ptr, cap, out.partial, out.counters, h->sm_count, h->host_live, &launches, st));
+    IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
+    h->ev_count++;
+    g_launches += launches;
+  } else {
+    const size_t smem = paths_smem_bytes(sc, 0);
+    const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, sc, smem);
     const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
     IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
     IPT_CUDA(launch_paths(MODE_RENDER_ID, sc, rp, out, grid, smem, st));
     IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
     h->ev_count++;
+    g_launches += 1;
   }
   IPT_CUDA(launch_resolve(out.partial, rp.n_pix, rp.groups, img_dev, img8_dev, st));
-  g_launches += 2;
+  g_launches += 1;
   return 0;
 }
 
@@ -425,6 +444,13 @@ void iptDefaultParams(IptRenderParams* p) {
 
 int iptSetAssetRoot(const char* root) { g_asset_root = root ? root : ""; return 0; }
 int iptSetDevice(int device) { g_device = device; return 0; }
+int iptSetIntegrator(int mode, int wavefront_slots) {
+  if (mode < 0 || mode > 2) return fail("integrator must be 0, 1 or 2");
+  if (wavefront_slots < 0) return fail("wavefront_slots must be >= 0");
+  g_integrator = mode;
+  g_wf_slots = wavefront_slots > 0 ? wavefront_slots : (1 << 24);
+  return 0;
+}
 int iptSetTraversalMode(int mode) {
   if (mode < 0 || mode > 2) return fail("traversal mode must be 0, 1 or 2");
   g_traversal_mode = mode;

@@ -15,6 +15,11 @@ size_t paths_smem_bytes(const DevScene& sc, int acc_floats);
 int paths_blocks_per_sm(int mode, const DevScene& sc, size_t smem);
 int paths_block_threads();   // threads per block of k_paths
 cudaError_t launch_paths(int mode, const DevScene& sc, const DevRender& rp, const DevOut& out, int grid, size_t smem, cudaStream_t st);
+// wavefront forward pass for BVH scenes: batches of <= cap paths, state in `workspace`; adds into `partial` exactly
+// what k_paths<RENDER> would write.  host_live: one pinned int (used only with unbounded depth).
+size_t wavefront_workspace_bytes(int cap);
+cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* workspace, int cap, float* partial, unsigned long long* counters,
+                             int sm_count, int* host_live, unsigned long long* n_launches, cudaStream_t st);
 cudaError_t launch_trace_rays(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter, int sm_count, cudaStream_t st);
 cudaError_t launch_trace_rays_stats(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter,
                                     unsigned long long* stats, int sm_count, cudaStream_t st);

@@ -31,7 +31,8 @@ EXPORTS = ["loadScene", "freeScene", "createImage", "createGraph", "getMaterials
            "iptSceneInfo", "iptGetTriangleTable", "iptGetCamera", "iptTraceRays", "iptTraceRaysDevice",
            "iptRender", "iptRenderDevice", "iptCreateImageEx", "iptCreateGraphEx", "iptGraphAccumulateDevice",
            "iptGraphCompress", "iptRenderGrad", "iptRenderGradDevice", "iptSetMaterialsDevice", "iptBuildBVH",
-           "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder", "iptTraceRaysStatsDevice"]
+           "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder", "iptTraceRaysStatsDevice",
+           "iptSetIntegrator"]
 
 
 def lib():
@@ -100,6 +101,13 @@ def default_params(**kw):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def set_integrator(mode=0, wavefront_slots=0):
+    """Forward integrator for BVH scenes: 0 auto (wavefront), 1 persistent megakernel, 2 wavefront;
+    wavefront_slots bounds the paths in flight per batch (0 = default)."""
+    if lib().iptSetIntegrator(int(mode), int(wavefront_slots)) != 0:
+        raise ValueError(last_error())
 
 
 def build_bvh(boxes, pos, leaf_size=4, builder=0):

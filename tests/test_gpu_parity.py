@@ -111,6 +111,35 @@ def test_forward_vertex_normals_and_bvh(ipt, oracle):
     assert img_g.tobytes() == img_o.tobytes()
 
 
+@pytest.mark.parametrize("scene,w,h,spp,depth,gs,slots", [("cornell_sphere", 48, 40, 70, 6, 32, 0), ("cornell_sphere", 48, 40, 70, 0, 32, 5000),
+                                                          ("cornell_sphere", 37, 29, 9, 5, 4, 700), ("scene0", 64, 48, 16, 0, 64, 1000),
+                                                          ("rotated_cubes", 48, 48, 8, 8, 3, 100000)])
+def test_wavefront_integrator_bit_exact(ipt, oracle, scene, w, h, spp, depth, gs, slots):
+    """BVH scenes render through the wavefront integrator (state in HBM, one closest-hit kernel per bounce);
+    it must reproduce the oracle -- and therefore the megakernel -- bit for bit, whatever the batch size
+    (slots < pixels forces pixel tiles, slots < pixels * group forces sample chunks) and with interleaved shards."""
+    objects = _scene0(oracle) if scene == "scene0" else scene_objects(scene)
+    g = ipt.Scene(objects, asset_root=ASSETS, traversal_mode=2)
+    o = oracle.OracleScene(objects, ASSETS)
+    assert g.uses_bvh
+    pg = ipt.default_params(width=w, height=h, spp=spp, max_depth=depth, seed=77, group_samples=gs)
+    po = oracle.make_params(w, h, spp, max_depth=depth, seed=77, group_samples=gs)
+    img_o, cnt_o = o.render(po)
+    try:
+        ipt.set_integrator(2, slots)
+        img_w, cnt_w = g.render(pg)
+        shard = ipt.default_params(width=w, height=h, spp=spp, max_depth=depth, seed=77, group_samples=gs, row_begin=1, row_end=h, row_step=3)
+        img_s, _ = g.render(shard)
+        ipt.set_integrator(1, 0)
+        img_m, cnt_m = g.render(pg)
+    finally:
+        ipt.set_integrator(0, 0)
+    assert cnt_w == cnt_o and cnt_m == cnt_o
+    assert img_w.tobytes() == img_o.tobytes(), "wavefront vs oracle: max abs diff %g" % np.abs(img_w - img_o).max()
+    assert img_m.tobytes() == img_o.tobytes()
+    assert img_s.tobytes() == img_o[1::3].tobytes()
+
+
 def test_row_sharding_and_determinism(ipt, oracle):
     g = ipt.Scene(_scene0(oracle), asset_root=ASSETS)
     p = ipt.default_params(width=96, height=80, spp=32, seed=3)

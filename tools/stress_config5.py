@@ -108,13 +108,20 @@ def main():
         nb, ni, perm = native.build_bvh(boxes, tab["center"], builder=2)
         print("iptBuildBVH (CUDA builder, incl. H2D/D2H of %.0f MB): %.3f s, %d nodes, depth levels ~%d" % (
             (boxes.nbytes + tab["center"].nbytes) / 1e6, time.time() - t0, ni.shape[0], int(np.ceil(np.log2(max(ni.shape[0], 2))))))
+    images = {}
+    for integ, name in ((1, "megakernel"), (2, "wavefront")):
+        ipt.set_integrator(integ, 0)
+        for rep in range(a.reps):
+            p = ipt.default_params(width=a.size, height=a.size, spp=a.spp, max_depth=a.depth, seed=rep)
+            img, cnt = sc.render(p)
+            ms = sc.kernel_times_ms(1)[0]
+            rays = cnt["ext_rays"] + cnt["shadow_rays"]
+            print("render [%s] %dx%dx%d depth %d: %s device %.1f ms -> %.1f Mrays/s, %.1f Mpaths/s, mean radiance %.4f" % (
+                name, a.size, a.size, a.spp, a.depth, cnt, ms, rays / ms / 1e3, cnt["paths"] / ms / 1e3, float(img.mean())))
+            images[(integ, rep)] = img
+    ipt.set_integrator(0, 0)
     for rep in range(a.reps):
-        p = ipt.default_params(width=a.size, height=a.size, spp=a.spp, max_depth=a.depth, seed=rep)
-        img, cnt = sc.render(p)
-        ms = sc.kernel_times_ms(1)[0]
-        rays = cnt["ext_rays"] + cnt["shadow_rays"]
-        print("render %dx%dx%d depth %d: %s kernel %.1f ms -> %.1f Mrays/s, %.1f Mpaths/s, mean radiance %.4f" % (
-            a.size, a.size, a.spp, a.depth, cnt, ms, rays / ms / 1e3, cnt["paths"] / ms / 1e3, float(img.mean())))
+        print("wavefront image == megakernel image (seed %d): %s" % (rep, images[(1, rep)].tobytes() == images[(2, rep)].tobytes()))
     # incoherent rays only: random origins inside the room, random directions
     rng = np.random.RandomState(0)
     n = 8_000_000
