@@ -70,14 +70,22 @@ def main():
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--cache-dir", default="", help="keep the generated OBJ files here and reuse them")
+    ap.add_argument("--only-render", type=int, default=0, help="1/2: render with that integrator only and exit (profiling)")
     a = ap.parse_args()
-    tmp = tempfile.mkdtemp(prefix="ipt_stress_")
+    tmp = a.cache_dir or tempfile.mkdtemp(prefix="ipt_stress_")
+    os.makedirs(tmp, exist_ok=True)
     t0 = time.time()
-    v, f = read_obj(os.path.join(ASSETS, "shapes", "sphere.obj"))
-    for _ in range(a.levels):
-        v, f = subdivide(v, f, 0.5)
-    sphere = os.path.join(tmp, "sphere_big.obj")
-    write_obj(sphere, v, f)
+    sphere = os.path.join(tmp, "sphere_big_%d.obj" % a.levels)
+    if not os.path.exists(sphere):
+        v, f = read_obj(os.path.join(ASSETS, "shapes", "sphere.obj"))
+        for _ in range(a.levels):
+            v, f = subdivide(v, f, 0.5)
+        write_obj(sphere + ".tmp", v, f)
+        os.replace(sphere + ".tmp", sphere)
+        n_tris, n_verts = f.shape[0], v.shape[0]
+    else:
+        n_tris = n_verts = -1
     # room: shapes/scene.obj; faces 17-18 (the ceiling patch) emissive through a synthetic MTL
     room_src = open(os.path.join(ASSETS, "shapes", "scene.obj")).read().splitlines()
     out, nf = ["mtllib room.mtl", "usemtl wall"], 0
@@ -90,7 +98,7 @@ def main():
     room = os.path.join(tmp, "room.obj")
     open(room, "w").write("\n".join(out) + "\n")
     open(os.path.join(tmp, "room.mtl"), "w").write("newmtl wall\nKd 0.7 0.7 0.7\nnewmtl lamp\nKd 0.7 0.7 0.7\nKe 10 10 10\n")
-    print("generated %d triangles (%d vertices) in %.1f s" % (f.shape[0], v.shape[0], time.time() - t0))
+    print("generated %d triangles (%d vertices) in %.1f s" % (n_tris, n_verts, time.time() - t0))
     objects = [{"pos": [0, 0, 0], "ori": [0, 0, 0], "scl": [1, 1, 1], "obj": room, "mtl": os.path.join(tmp, "room.mtl")},
                {"pos": [0, -0.5, 3], "ori": [0, 0, 0], "scl": [2, 2, 2], "obj": sphere, "mtl": "*Kd 0.8 0.6 0.3*"}]
     L = native.lib()
@@ -100,6 +108,14 @@ def main():
     t_load = time.time() - t0
     print("loadScene: %.2f s total (OBJ parse + triangle setup + GPU BVH build + upload); nT=%d nE=%d nodes=%d bvh=%d; %d kernel launches" % (
         t_load, sc.nT, sc.nE, sc.n_nodes, sc.uses_bvh, L.iptKernelLaunchCount() - k0))
+    if a.only_render:
+        ipt.set_integrator(a.only_render, 0)
+        for rep in range(a.reps):
+            p = ipt.default_params(width=a.size, height=a.size, spp=a.spp, max_depth=a.depth, seed=rep)
+            img, cnt = sc.render(p)
+            ms = sc.kernel_times_ms(1)[0]
+            print("render [integrator %d] %s device %.1f ms -> %.1f Mrays/s" % (a.only_render, cnt, ms, (cnt["ext_rays"] + cnt["shadow_rays"]) / ms / 1e3))
+        return
     # BVH build alone on the same primitives (host arrays -> CUDA builder -> host arrays)
     tab = sc.triangle_table()
     boxes = np.concatenate([tab["verts"].min(1), tab["verts"].max(1)], 1)
