@@ -339,6 +339,11 @@ static int upload_scene(SceneHandle* h) {
     IPT_CUDA(cudaMalloc(&h->bvh_prims, perm.size() * sizeof(int)));
     IPT_CUDA(cudaMemcpy(h->bvh_nodes, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice));
     IPT_CUDA(cudaMemcpy(h->bvh_prims, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // leaf triangles are read in tree order: store their records that way (slot j = triangle perm[j]), so a leaf is
+    // one contiguous run and the id lookup is only needed for accepted hits
+    std::vector<float4> leaf_geom(4 * nT);
+    for (size_t j = 0; j < nT; j++) memcpy(&leaf_geom[4 * j], &geom[4 * (size_t)perm[j]], 4 * sizeof(float4));
+    IPT_CUDA(cudaMemcpy(h->geom, leaf_geom.data(), leaf_geom.size() * sizeof(float4), cudaMemcpyHostToDevice));
   }
   return 0;
 }

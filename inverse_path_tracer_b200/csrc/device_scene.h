@@ -26,7 +26,7 @@ enum : int { TRI_HAS_VN = 1, TRI_SPECULAR = 2, TRI_ANY_KS = 4, TRI_NEG_Z = 8 /* 
 constexpr int kMatStride = 8;   // float4 records per triangle in `mat`
 
 struct DevScene {
-  const float4* geom;
+  const float4* geom;          // [4 nT] plane + 3 edge planes per triangle; in BVH scenes stored in leaf order (slot j = triangle bvh_prims[j])
   const float4* planes;
   const int2* grange;
   const float4* slot_edges;

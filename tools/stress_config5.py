@@ -70,6 +70,7 @@ def main():
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--sort-rays", type=int, default=0, help="sort the incoherent test rays by an n-bit Morton cell + octant first")
     ap.add_argument("--cache-dir", default="", help="keep the generated OBJ files here and reuse them")
     ap.add_argument("--only-render", type=int, default=0, help="1/2: render with that integrator only and exit (profiling)")
     a = ap.parse_args()
@@ -108,7 +109,9 @@ def main():
     t_load = time.time() - t0
     print("loadScene: %.2f s total (OBJ parse + triangle setup + GPU BVH build + upload); nT=%d nE=%d nodes=%d bvh=%d; %d kernel launches" % (
         t_load, sc.nT, sc.nE, sc.n_nodes, sc.uses_bvh, L.iptKernelLaunchCount() - k0))
-    if a.only_render:
+    if a.only_render == 3:
+        pass
+    elif a.only_render:
         ipt.set_integrator(a.only_render, 0)
         for rep in range(a.reps):
             p = ipt.default_params(width=a.size, height=a.size, spp=a.spp, max_depth=a.depth, seed=rep)
@@ -116,6 +119,12 @@ def main():
             ms = sc.kernel_times_ms(1)[0]
             print("render [integrator %d] %s device %.1f ms -> %.1f Mrays/s" % (a.only_render, cnt, ms, (cnt["ext_rays"] + cnt["shadow_rays"]) / ms / 1e3))
         return
+    if a.only_render != 3:
+        bvh_and_render(a, sc, L)
+    trace_test(a, sc, L)
+
+
+def bvh_and_render(a, sc, L):
     # BVH build alone on the same primitives (host arrays -> CUDA builder -> host arrays)
     tab = sc.triangle_table()
     boxes = np.concatenate([tab["verts"].min(1), tab["verts"].max(1)], 1)
@@ -138,12 +147,26 @@ def main():
     ipt.set_integrator(0, 0)
     for rep in range(a.reps):
         print("wavefront image == megakernel image (seed %d): %s" % (rep, images[(1, rep)].tobytes() == images[(2, rep)].tobytes()))
+
+
+def trace_test(a, sc, L):
     # incoherent rays only: random origins inside the room, random directions
     rng = np.random.RandomState(0)
     n = 8_000_000
     d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
     o = rng.uniform([-1.9, -1.9, 1.1], [1.9, 1.9, 4.9], (n, 3))
     rays = np.concatenate([o, d], 1).astype(np.float32)
+    if a.sort_rays:
+        # origin cell (Morton order, 2^bits cells per axis) then direction octant: what a device-side ray sort would produce
+        bits = a.sort_rays
+        q = np.clip(((o - [-2, -2, 1]) / 4.0 * (1 << bits)).astype(np.int64), 0, (1 << bits) - 1)
+        key = np.zeros(n, np.int64)
+        for b in range(bits):
+            for ax in range(3):
+                key |= ((q[:, ax] >> b) & 1) << (3 * b + ax)
+        key = (key << 3) | ((d[:, 0] > 0).astype(np.int64) | ((d[:, 1] > 0).astype(np.int64) << 1) | ((d[:, 2] > 0).astype(np.int64) << 2))
+        rays = rays[np.argsort(key, kind="stable")]
+        print("rays sorted by %d-bit Morton cell + octant" % bits)
     import torch
     from inverse_path_tracer_b200.torch_api import TorchScene  # noqa: F401
     import ctypes as C
