@@ -366,6 +366,33 @@ def b200_arm(args):
                                                                "ms_per_iter_per_gpu": bms / iters, "loss_after_rank0": float(lastb.detach())}
         mine.close()
         inv.close()
+        # ---- BVH scenes (BASELINE config 5 at bench scale): room + 327 680-triangle sphere, wavefront integrator;
+        #      rank 0 of a single-GPU run only (the stress tool runs the 5.2 M-triangle version)
+        if world == 1:
+            import importlib.util
+            import tempfile
+            spec = importlib.util.spec_from_file_location("stress_config5", os.path.join(ROOT, "tools", "stress_config5.py"))
+            stress = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(stress)
+            sobjs, sphere_tris = stress.stress_scene_objects(4, tempfile.mkdtemp(prefix="ipt_bench_"))
+            bs = TorchScene(sobjs, asset_root=ASSETS, device=local)
+            bout = torch.empty((1024, 1024, 3), dtype=torch.float32, device=dev)
+            bp = lambda s_: ipt.default_params(width=1024, height=1024, spp=4, max_depth=8, seed=s_)
+            for i in range(2):
+                bs.render(bp(50 + i), out=bout, counters=counters)
+            total.zero_()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for i in range(5):
+                bs.render(bp(i), out=bout, counters=counters)
+                total.add_(counters)
+            v1.record()
+            torch.cuda.synchronize()
+            vms = v0.elapsed_time(v1)
+            vc = [int(x) for x in total.tolist()]
+            extra["bvh_room_sphere_1024x1024_4spp_depth8"] = {"triangles": int(bs.nT), "integrator": "wavefront", "mrays_per_s": (vc[1] + vc[2]) / (vms * 1e-3) / 1e6,
+                                                              "mpaths_per_s": vc[0] / (vms * 1e-3) / 1e6, "ms_per_frame": vms / 5}
+            bs.close()
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -------------------------------------
     cpu = None

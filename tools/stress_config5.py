@@ -63,30 +63,19 @@ def write_obj(path, v, f, normals=True):
         fh.write("\n")
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--levels", type=int, default=6)
-    ap.add_argument("--size", type=int, default=1024)
-    ap.add_argument("--spp", type=int, default=16)
-    ap.add_argument("--depth", type=int, default=8)
-    ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--sort-rays", type=int, default=0, help="sort the incoherent test rays by an n-bit Morton cell + octant first")
-    ap.add_argument("--cache-dir", default="", help="keep the generated OBJ files here and reuse them")
-    ap.add_argument("--only-render", type=int, default=0, help="1/2: render with that integrator only and exit (profiling)")
-    a = ap.parse_args()
-    tmp = a.cache_dir or tempfile.mkdtemp(prefix="ipt_stress_")
+def stress_scene_objects(levels, cache_dir=""):
+    """write the config-5 assets (room with an emissive ceiling patch + subdivided sphere) and return
+    (object list for ipt.Scene, sphere triangle count)"""
+    tmp = cache_dir or tempfile.mkdtemp(prefix="ipt_stress_")
     os.makedirs(tmp, exist_ok=True)
-    t0 = time.time()
-    sphere = os.path.join(tmp, "sphere_big_%d.obj" % a.levels)
+    sphere = os.path.join(tmp, "sphere_big_%d.obj" % levels)
     if not os.path.exists(sphere):
         v, f = read_obj(os.path.join(ASSETS, "shapes", "sphere.obj"))
-        for _ in range(a.levels):
+        for _ in range(levels):
             v, f = subdivide(v, f, 0.5)
         write_obj(sphere + ".tmp", v, f)
         os.replace(sphere + ".tmp", sphere)
-        n_tris, n_verts = f.shape[0], v.shape[0]
-    else:
-        n_tris = n_verts = -1
+    n_tris = 1280 * 4 ** levels
     # room: shapes/scene.obj; faces 17-18 (the ceiling patch) emissive through a synthetic MTL
     room_src = open(os.path.join(ASSETS, "shapes", "scene.obj")).read().splitlines()
     out, nf = ["mtllib room.mtl", "usemtl wall"], 0
@@ -99,9 +88,25 @@ def main():
     room = os.path.join(tmp, "room.obj")
     open(room, "w").write("\n".join(out) + "\n")
     open(os.path.join(tmp, "room.mtl"), "w").write("newmtl wall\nKd 0.7 0.7 0.7\nnewmtl lamp\nKd 0.7 0.7 0.7\nKe 10 10 10\n")
-    print("generated %d triangles (%d vertices) in %.1f s" % (n_tris, n_verts, time.time() - t0))
     objects = [{"pos": [0, 0, 0], "ori": [0, 0, 0], "scl": [1, 1, 1], "obj": room, "mtl": os.path.join(tmp, "room.mtl")},
                {"pos": [0, -0.5, 3], "ori": [0, 0, 0], "scl": [2, 2, 2], "obj": sphere, "mtl": "*Kd 0.8 0.6 0.3*"}]
+    return objects, n_tris
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--levels", type=int, default=6)
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--depth", type=int, default=8)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--sort-rays", type=int, default=0, help="sort the incoherent test rays by an n-bit Morton cell + octant first")
+    ap.add_argument("--cache-dir", default="", help="keep the generated OBJ files here and reuse them")
+    ap.add_argument("--only-render", type=int, default=0, help="1/2: render with that integrator only and exit (profiling)")
+    a = ap.parse_args()
+    t0 = time.time()
+    objects, n_tris = stress_scene_objects(a.levels, a.cache_dir)
+    print("generated %d sphere triangles in %.1f s" % (n_tris, time.time() - t0))
     L = native.lib()
     k0 = L.iptKernelLaunchCount()
     t0 = time.time()
