@@ -56,7 +56,12 @@ typedef struct IptRenderParams {
   int max_depth;          /* <= 0: unbounded like the reference; else max radiance() calls per path */
   float p_rr;             /* scene.h:11    (.9f)       */
   uint32_t seed_lo, seed_hi;   /* Philox key */
-  int group_samples;      /* samples accumulated sequentially per partial sum (<= 0: spp) */
+  int group_samples;      /* samples accumulated sequentially per partial sum; a pixel is the sum of its group partials in
+                           * group order.  0 (or > spp): spp, i.e. the reference's single running sum (path_trace.cu:190-193).
+                           * -1 (the default): chosen from the FULL image size only, so every shard of an image agrees:
+                           * the largest g in {64, 32, 16, 8, 4} with width * height * spp >= g * 2^20 (else 4).  A group is
+                           * the unit of work the persistent kernel hands to a lane: small jobs need small groups to fill
+                           * the GPU, large jobs prefer 64 (fewer partials). */
   int row_begin, row_end; /* pixel-row shard [begin, end); row_end <= 0 means height */
   int row_step;           /* every row_step-th row of the shard, starting at row_begin (<= 1: every row).  Interleaved
                            * shards (begin = rank, step = world) balance the load across GPUs; outputs are compact */

@@ -370,7 +370,12 @@ static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan)
   rp.two_over_w = 2.0f / (float)p->width;
   rp.two_over_h = 2.0f / (float)p->height;
   rp.c_diff = (1.0f / 0.318309873f) / p->p_rr;   // canon v2: diffuse coeff = cos * ((1 / (1/pi)) / p_rr), path_trace.cu:137
-  rp.group_samples = (p->group_samples <= 0 || p->group_samples > p->spp) ? p->spp : p->group_samples;
+  int gs = p->group_samples;
+  if (gs < 0) {   // auto (include/ipt_b200.h): depends on the full image size only
+    gs = 64;
+    while (gs > 4 && (long long)p->width * p->height * p->spp < ((long long)gs << 20)) gs >>= 1;
+  }
+  rp.group_samples = (gs <= 0 || gs > p->spp) ? p->spp : gs;
   rp.groups = (p->spp + rp.group_samples - 1) / rp.group_samples;
   const int step = p->row_step < 1 ? 1 : p->row_step;
   const int rows = (re - rb + step - 1) / step;
@@ -443,7 +448,7 @@ void iptDefaultParams(IptRenderParams* p) {
   p->max_depth = 0;
   p->p_rr = 0.9f;                                  // scene.h:11
   p->seed_lo = 0; p->seed_hi = 0;
-  p->group_samples = 64;
+  p->group_samples = -1;
   p->row_begin = 0; p->row_end = 0; p->row_step = 1;
 }
 

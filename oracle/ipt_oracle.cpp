@@ -797,7 +797,7 @@ struct Params {
   int width, height, spp, max_depth;   // max_depth <= 0: unbounded (reference behaviour)
   float p_rr;                          // scene.h:11 (.9f)
   uint32_t seed_lo, seed_hi;
-  int group_samples;                   // samples summed sequentially per partial (<=0: spp)
+  int group_samples;                   // samples summed sequentially per partial (0: spp, -1: size rule)
   int row_begin, row_end;              // rows rendered [begin,end) (pixel-row sharding)
   int row_step;                        // every row_step-th row of that range (interleaved shards)
 };
@@ -1005,7 +1005,15 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
   }
 }
 
-static inline int group_size(const Params& P) { return (P.group_samples <= 0 || P.group_samples > P.spp) ? P.spp : P.group_samples; }
+// include/ipt_b200.h, IptRenderParams::group_samples: 0 = one running sum like the reference, -1 = size rule
+static inline int group_size(const Params& P) {
+  int gs = P.group_samples;
+  if (gs < 0) {
+    gs = 64;
+    while (gs > 4 && (long long)P.width * P.height * P.spp < ((long long)gs << 20)) gs >>= 1;
+  }
+  return (gs <= 0 || gs > P.spp) ? P.spp : gs;
+}
 
 // pixel mean: toneMap's sum  sum_i src[i]/SPP  (path_trace.cu:190-193), in groups of
 // `group_samples` consecutive samples; group partials are then added in group order.

@@ -20,7 +20,7 @@ class OrcParams(C.Structure):
                 ("group_samples", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("row_step", C.c_int)]
 
 
-def make_params(width=500, height=500, spp=100, max_depth=0, p_rr=0.9, seed=0, group_samples=64,
+def make_params(width=500, height=500, spp=100, max_depth=0, p_rr=0.9, seed=0, group_samples=-1,
                 row_begin=0, row_end=0, row_step=1):
     return OrcParams(width, height, spp, max_depth, p_rr, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF,
                      group_samples, row_begin, row_end, row_step)

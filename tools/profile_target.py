@@ -23,6 +23,8 @@ ap.add_argument("--depth", type=int, default=8)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--mode", default="render")
 ap.add_argument("--traversal", type=int, default=0)
+ap.add_argument("--group", type=int, default=-1)
+ap.add_argument("--row-step", type=int, default=1)
 a = ap.parse_args()
 if a.scene == "cornell":
     objs = [{"pos": [0, 0, 4], "ori": [0, 0, 0], "scl": [2, 2, 2], "obj": "./CornellBox/CornellBox-Empty-CO.obj", "mtl": "./CornellBox/CornellBox-Empty-CO.mtl"}]
@@ -32,7 +34,7 @@ sc = ipt.Scene(objs, asset_root=ASSETS, traversal_mode=a.traversal)
 rng = np.random.RandomState(0)
 target = rng.randint(0, 256, (a.size, a.size, 3)).astype(np.uint8)
 for i in range(a.reps):
-    p = ipt.default_params(width=a.size, height=a.size, spp=a.spp, max_depth=a.depth, seed=i)
+    p = ipt.default_params(width=a.size, height=a.size, spp=a.spp, max_depth=a.depth, seed=i, group_samples=a.group, row_begin=0, row_end=a.size, row_step=a.row_step)
     if a.mode == "render":
         img, cnt = sc.render(p)
     elif a.mode == "graph":
