@@ -133,6 +133,7 @@ void read_mtl(std::istream& in, MtlLibrary* lib) {
   HostMaterial cur;
   std::string cur_name;
   bool seen_d = false;
+  bool seen_kd = false;   // like the reference (material.h:396-398, 447-448) this one is NOT reset by newmtl
   std::string line;
   auto flush = [&]() {
     lib->by_name.insert(std::make_pair(cur_name, (int)lib->mats.size()));
@@ -150,7 +151,8 @@ void read_mtl(std::istream& in, MtlLibrary* lib) {
       seen_d = false;
       sc.advance(1);
       cur_name = sc.rest();
-    } else if (sc.keyword("Kd")) { sc.real3(cur.kd);
+    } else if (sc.keyword("Kd")) { sc.real3(cur.kd); seen_kd = true;
+    } else if (sc.keyword("map_Kd")) { if (!seen_kd) cur.kd[0] = cur.kd[1] = cur.kd[2] = 0.6f;   // material.h:630-641
     } else if (sc.keyword("Ks")) { sc.real3(cur.ks);
     } else if (sc.keyword("Ke")) { sc.real3(cur.ke);
     } else if (sc.keyword("Kt") || sc.keyword("Tf")) { sc.real3(cur.kt);
@@ -171,12 +173,118 @@ struct ObjMesh {
   MtlLibrary lib;
 };
 
+// ---- polygons -> triangles ---------------------------------------------------------------------------
+// What exportGroupsToShape does with triangulate = true (tiny_obj_loader.h:180-566), including the parts
+// that only matter for odd input: faces wait in their group until the group is flushed (`g`, `o`, a usemtl
+// that changes the material, end of file) and are range-checked against the vertex array of THAT moment;
+// quads split along the shorter diagonal; polygons with more corners are ear-clipped in a 2-D projection.
+class FaceGroup {
+ public:
+  void add(const std::vector<int>& corners, int material) {
+    if (corners.size() < 3) return;
+    first_.push_back((int)idx_.size());
+    count_.push_back((int)corners.size());
+    mat_.push_back(material);
+    idx_.insert(idx_.end(), corners.begin(), corners.end());
+  }
+  void flush(const std::vector<float>& v, ObjMesh* out) {
+    for (size_t f = 0; f < first_.size(); f++) emit_face(&idx_[first_[f]], count_[f], mat_[f], v, out);
+    first_.clear(); count_.clear(); mat_.clear(); idx_.clear();
+  }
+
+ private:
+  std::vector<int> first_, count_, mat_, idx_;
+
+  static bool readable(const std::vector<float>& v, int vertex, size_t component) {
+    return (size_t)vertex * 3 + component < v.size();   // a negative index wraps and fails
+  }
+  static void tri(ObjMesh* out, int a, int b, int c, int material) {
+    out->tri_v.push_back(a); out->tri_v.push_back(b); out->tri_v.push_back(c);
+    out->tri_mat.push_back(material);
+  }
+  // crossing-number test against the candidate ear (material.h:369-381)
+  static bool inside_ear(const float x[3], const float y[3], float qx, float qy) {
+    int crossings = 0;
+    int j = 2;
+    for (int i = 0; i < 3; j = i, i++) {
+      const bool straddles = (y[i] > qy) != (y[j] > qy);
+      if (straddles && qx < (x[j] - x[i]) * (qy - y[i]) / (y[j] - y[i]) + x[i]) crossings ^= 1;
+    }
+    return crossings != 0;
+  }
+  static void emit_face(const int* c, int n, int material, const std::vector<float>& v, ObjMesh* out) {
+    if (n == 3) { tri(out, c[0], c[1], c[2], material); return; }
+    if (n == 4) {
+      for (int k = 0; k < 4; k++) if (!readable(v, c[k], 2)) return;
+      const float* a = &v[3 * (size_t)c[0]]; const float* b = &v[3 * (size_t)c[1]];
+      const float* cc = &v[3 * (size_t)c[2]]; const float* d = &v[3 * (size_t)c[3]];
+      // shorter diagonal, plain float arithmetic in the reference's order (tiny_obj_loader.h:257-265)
+      float acx = cc[0] - a[0], acy = cc[1] - a[1], acz = cc[2] - a[2];
+      float bdx = d[0] - b[0], bdy = d[1] - b[1], bdz = d[2] - b[2];
+      float len_ac = acx * acx + acy * acy + acz * acz;
+      float len_bd = bdx * bdx + bdy * bdy + bdz * bdz;
+      if (len_ac < len_bd) { tri(out, c[0], c[1], c[2], material); tri(out, c[0], c[2], c[3], material); }
+      else { tri(out, c[0], c[1], c[3], material); tri(out, c[1], c[2], c[3], material); }
+      return;
+    }
+    // projection plane from the first corner that is not degenerate (tiny_obj_loader.h:314-361)
+    size_t ua = 1, va = 2;
+    for (int k = 0; k < n; k++) {
+      const int i0 = c[k], i1 = c[(k + 1) % n], i2 = c[(k + 2) % n];
+      if (!(readable(v, i0, 2) && readable(v, i1, 2) && readable(v, i2, 2))) continue;
+      const float* p0 = &v[3 * (size_t)i0]; const float* p1 = &v[3 * (size_t)i1]; const float* p2 = &v[3 * (size_t)i2];
+      const float ax = p1[0] - p0[0], ay = p1[1] - p0[1], az = p1[2] - p0[2];
+      const float bx = p2[0] - p1[0], by = p2[1] - p1[1], bz = p2[2] - p1[2];
+      const float nx = fabsf(ay * bz - az * by), ny = fabsf(az * bx - ax * bz), nz = fabsf(ax * by - ay * bx);
+      const float tiny = 1.1920929e-07f;   // numeric_limits<float>::epsilon()
+      if (nx > tiny || ny > tiny || nz > tiny) {
+        const bool x_dominates = nx > ny && nx > nz;
+        if (!x_dominates) {
+          ua = 0;
+          if (nz > nx && nz > ny) va = 1;
+        }
+        break;
+      }
+    }
+    // ear clipping (tiny_obj_loader.h:421-564): `at` walks the ring; a full round without an ear ends the face
+    // and whatever is left of it is dropped
+    std::vector<int> ring(c, c + n);
+    size_t at = 0, tries_left = (size_t)n, last_size = (size_t)n;
+    while (ring.size() > 3 && tries_left > 0) {
+      const size_t m = ring.size();
+      if (at >= m) at -= m;
+      if (last_size != m) { last_size = m; tries_left = m; } else { tries_left--; }
+      int ear[3];
+      float x[3], y[3];
+      for (int k = 0; k < 3; k++) {
+        ear[k] = ring[(at + k) % m];
+        const bool ok = readable(v, ear[k], ua) && readable(v, ear[k], va);
+        x[k] = ok ? v[(size_t)ear[k] * 3 + ua] : 0.0f;
+        y[k] = ok ? v[(size_t)ear[k] * 3 + va] : 0.0f;
+      }
+      const float turn = (x[1] - x[0]) * (y[2] - y[1]) - (y[1] - y[0]) * (x[2] - x[1]);
+      const float signed_half = (x[0] * y[1] - y[0] * x[1]) * 0.5f;   // the reference's "area": corners 0 and 1 only
+      bool is_ear = !(turn * signed_half < 0.0f);
+      for (size_t o = 3; is_ear && o < m; o++) {
+        const int q = ring[(at + o) % m];
+        if (!(readable(v, q, ua) && readable(v, q, va))) continue;
+        if (inside_ear(x, y, v[(size_t)q * 3 + ua], v[(size_t)q * 3 + va])) is_ear = false;
+      }
+      if (!is_ear) { at++; continue; }
+      tri(out, ear[0], ear[1], ear[2], material);
+      ring.erase(ring.begin() + (std::ptrdiff_t)((at + 1) % m));
+    }
+    if (ring.size() == 3) tri(out, ring[0], ring[1], ring[2], material);
+  }
+};
+
 bool read_obj(const std::string& path, const std::string& mtl_arg, bool mtl_is_inline, ObjMesh* out, std::string* err) {
   std::ifstream in(path.c_str());
   if (!in) { *err = "Object File was not able to be opened: '" + path + "' (" + strerror(errno) + ")"; return false; }
   int active = -1;
   bool mtl_read = false;
   std::vector<int> poly;
+  FaceGroup group;
   std::string line;
   size_t line_no = 0;
   while (std::getline(in, line)) {
@@ -200,40 +308,16 @@ bool read_obj(const std::string& path, const std::string& mtl_arg, bool mtl_is_i
         poly.push_back(raw > 0 ? raw - 1 : nv + raw);
         sc.skip_blanks();
       }
-      const size_t n = poly.size();
-      if (n < 3) continue;
-      if (n == 3) {
-        out->tri_v.insert(out->tri_v.end(), poly.begin(), poly.end());
-        out->tri_mat.push_back(active);
-      } else if (n == 4) {
-        bool in_range = true;
-        for (int k = 0; k < 4; k++) in_range = in_range && poly[k] >= 0 && (size_t)(3 * poly[k] + 2) < out->v.size();
-        if (!in_range) continue;
-        const float* a = &out->v[3 * poly[0]]; const float* b = &out->v[3 * poly[1]];
-        const float* c = &out->v[3 * poly[2]]; const float* d = &out->v[3 * poly[3]];
-        // shorter diagonal, plain float arithmetic in the reference's order (tiny_obj_loader.h:257-265)
-        float acx = c[0] - a[0], acy = c[1] - a[1], acz = c[2] - a[2];
-        float bdx = d[0] - b[0], bdy = d[1] - b[1], bdz = d[2] - b[2];
-        float len_ac = acx * acx + acy * acy + acz * acz;
-        float len_bd = bdx * bdx + bdy * bdy + bdz * bdz;
-        const int split_ac[6] = {0, 1, 2, 0, 2, 3}, split_bd[6] = {0, 1, 3, 1, 2, 3};
-        const int* pick = (len_ac < len_bd) ? split_ac : split_bd;
-        for (int k = 0; k < 6; k++) out->tri_v.push_back(poly[pick[k]]);
-        out->tri_mat.push_back(active);
-        out->tri_mat.push_back(active);
-      } else {
-        // DEVIATION (documented in DESIGN.md): polygons with more than 4 vertices are fanned; the
-        // reference ear-clips them (tiny_obj_loader.h:310-564).  No shipped asset has one.
-        for (size_t k = 1; k + 1 < n; k++) {
-          out->tri_v.push_back(poly[0]); out->tri_v.push_back(poly[k]); out->tri_v.push_back(poly[k + 1]);
-          out->tri_mat.push_back(active);
-        }
-      }
+      group.add(poly, active);
     } else if (sc.prefix("usemtl")) {
       sc.advance(6);
       std::string name = sc.word();
       std::map<std::string, int>::const_iterator it = out->lib.by_name.find(name);
-      active = (it == out->lib.by_name.end()) ? -1 : it->second;
+      const int next = (it == out->lib.by_name.end()) ? -1 : it->second;
+      if (next != active) group.flush(out->v, out);
+      active = next;
+    } else if (sc.keyword("g") || sc.keyword("o")) {
+      group.flush(out->v, out);
     } else if (sc.keyword("mtllib")) {
       // the file name on this line is ignored: the reference always reads the MTL stream it was
       // handed (MaterialStreamReader, material.h:784-809 <- scene_basics.h:224-225)
@@ -244,6 +328,7 @@ bool read_obj(const std::string& path, const std::string& mtl_arg, bool mtl_is_i
       }
     }
   }
+  group.flush(out->v, out);
   return true;
 }
 

@@ -35,6 +35,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <limits>
 #include <map>
 #include <sstream>
 #include <string>
@@ -256,6 +257,7 @@ struct Material {
 static void load_mtl(std::istream& in, std::vector<Material>* mats, std::map<std::string, int>* mat_map) {
   Material m;
   bool has_d = false, has_tr = false;
+  bool has_kd = false;   // material.h:396-398; set by any Kd and -- unlike has_d / has_tr -- NOT reset by newmtl (material.h:447-448)
   std::string line;
   while (std::getline(in, line)) {
     size_t last = line.find_last_not_of(" \t\r\n");
@@ -274,7 +276,9 @@ static void load_mtl(std::istream& in, std::vector<Material>* mats, std::map<std
       m.name = std::string(tok + 7);
       continue;
     }
-    if (tok[0] == 'K' && tok[1] == 'd' && is_space(tok[2])) { tok += 2; parse_real3(&m.kd[0], &m.kd[1], &m.kd[2], &tok); continue; }
+    if (tok[0] == 'K' && tok[1] == 'd' && is_space(tok[2])) { tok += 2; parse_real3(&m.kd[0], &m.kd[1], &m.kd[2], &tok); has_kd = true; continue; }
+    // a diffuse texture without a Kd seen so far gives the material Kd = 0.6 (material.h:630-641)
+    if (0 == strncmp(tok, "map_Kd", 6) && is_space(tok[6])) { if (!has_kd) m.kd[0] = m.kd[1] = m.kd[2] = 0.6f; continue; }
     if (tok[0] == 'K' && tok[1] == 's' && is_space(tok[2])) { tok += 2; parse_real3(&m.ks[0], &m.ks[1], &m.ks[2], &tok); continue; }
     if (tok[0] == 'K' && tok[1] == 'e' && is_space(tok[2])) { tok += 2; parse_real3(&m.ke[0], &m.ke[1], &m.ke[2], &tok); continue; }
     if ((tok[0] == 'K' && tok[1] == 't' && is_space(tok[2])) || (tok[0] == 'T' && tok[1] == 'f' && is_space(tok[2]))) {
@@ -315,6 +319,90 @@ static bool parse_face_vertex(const char** tok, int vsize, int* v_idx) {
   return true;
 }
 
+// point-in-polygon by crossing number (material.h:369-381), float arithmetic in that order
+static bool crossing_inside(const float* px, const float* py, int n, float tx, float ty) {
+  bool in = false;
+  for (int i = 0, j = n - 1; i < n; j = i++) {
+    if (((py[i] > ty) != (py[j] > ty)) && (tx < (px[j] - px[i]) * (ty - py[i]) / (py[j] - py[i]) + px[i])) in = !in;
+  }
+  return in;
+}
+
+// One face -> triangles, as exportGroupsToShape does with triangulate = true (tiny_obj_loader.h:180-566):
+// triangles pass through; quads split along the shorter diagonal (squared lengths, plain float sums; the quad is
+// dropped when an index is out of range); larger polygons are ear-clipped in the 2-D projection that drops the
+// dominant axis of the first non-degenerate corner, with the reference's quirks kept: the "area" sign uses
+// corners 0 and 1 only, out-of-range coordinates read as 0, and when no ear is found for a full round the
+// rest of the polygon is discarded.  `v` is the vertex array as it stands when the group is flushed.
+static void triangulate_face(const std::vector<int>& vi, int mat, const std::vector<float>& v, ObjData* out) {
+  const size_t n = vi.size();
+  auto emit = [&](int a, int b, int c) {
+    out->face_v.push_back(a); out->face_v.push_back(b); out->face_v.push_back(c);
+    out->face_mat.push_back(mat);
+  };
+  if (n < 3) return;
+  if (n == 3) { emit(vi[0], vi[1], vi[2]); return; }
+  auto in_range = [&](int idx, size_t comp) { return ((size_t)idx * 3 + comp) < v.size(); };   // negative ids wrap to huge values
+  if (n == 4) {
+    for (int k = 0; k < 4; k++) if (!in_range(vi[k], 2)) return;
+    const float* p0 = &v[3 * (size_t)vi[0]]; const float* p1 = &v[3 * (size_t)vi[1]];
+    const float* p2 = &v[3 * (size_t)vi[2]]; const float* p3 = &v[3 * (size_t)vi[3]];
+    float e02x = p2[0] - p0[0], e02y = p2[1] - p0[1], e02z = p2[2] - p0[2];
+    float e13x = p3[0] - p1[0], e13y = p3[1] - p1[1], e13z = p3[2] - p1[2];
+    float sqr02 = e02x * e02x + e02y * e02y + e02z * e02z;
+    float sqr13 = e13x * e13x + e13y * e13y + e13z * e13z;
+    if (sqr02 < sqr13) { emit(vi[0], vi[1], vi[2]); emit(vi[0], vi[2], vi[3]); }
+    else { emit(vi[0], vi[1], vi[3]); emit(vi[1], vi[2], vi[3]); }
+    return;
+  }
+  size_t ax0 = 1, ax1 = 2;
+  for (size_t k = 0; k < n; k++) {
+    const int a = vi[k % n], b = vi[(k + 1) % n], c = vi[(k + 2) % n];
+    if (!in_range(a, 2) || !in_range(b, 2) || !in_range(c, 2)) continue;
+    const float* pa = &v[3 * (size_t)a]; const float* pb = &v[3 * (size_t)b]; const float* pc = &v[3 * (size_t)c];
+    float e0x = pb[0] - pa[0], e0y = pb[1] - pa[1], e0z = pb[2] - pa[2];
+    float e1x = pc[0] - pb[0], e1y = pc[1] - pb[1], e1z = pc[2] - pb[2];
+    float cx = std::fabs(e0y * e1z - e0z * e1y), cy = std::fabs(e0z * e1x - e0x * e1z), cz = std::fabs(e0x * e1y - e0y * e1x);
+    const float eps = std::numeric_limits<float>::epsilon();
+    if (cx > eps || cy > eps || cz > eps) {
+      if (!(cx > cy && cx > cz)) {
+        ax0 = 0;
+        if (cz > cx && cz > cy) ax1 = 1;
+      }
+      break;
+    }
+  }
+  std::vector<int> rest = vi;
+  size_t guess = 0, budget = n, prev = n;
+  while (rest.size() > 3 && budget > 0) {
+    const size_t m = rest.size();
+    if (guess >= m) guess -= m;
+    if (prev != m) { prev = m; budget = m; } else budget--;
+    int c3[3];
+    float px[3], py[3];
+    for (size_t k = 0; k < 3; k++) {
+      c3[k] = rest[(guess + k) % m];
+      const bool ok = in_range(c3[k], ax0) && in_range(c3[k], ax1);
+      px[k] = ok ? v[(size_t)c3[k] * 3 + ax0] : 0.0f;
+      py[k] = ok ? v[(size_t)c3[k] * 3 + ax1] : 0.0f;
+    }
+    const float e0x = px[1] - px[0], e0y = py[1] - py[0], e1x = px[2] - px[1], e1y = py[2] - py[1];
+    const float cross = e0x * e1y - e0y * e1x;
+    const float area = (px[0] * py[1] - py[0] * px[1]) * 0.5f;
+    if (cross * area < 0.0f) { guess++; continue; }       // reflex corner in the projection
+    bool blocked = false;
+    for (size_t o = 3; o < m && !blocked; o++) {
+      const int q = rest[(guess + o) % m];
+      if (!in_range(q, ax0) || !in_range(q, ax1)) continue;
+      blocked = crossing_inside(px, py, 3, v[(size_t)q * 3 + ax0], v[(size_t)q * 3 + ax1]);
+    }
+    if (blocked) { guess++; continue; }
+    emit(c3[0], c3[1], c3[2]);
+    rest.erase(rest.begin() + (long)((guess + 1) % m));
+  }
+  if (rest.size() == 3) emit(rest[0], rest[1], rest[2]);
+}
+
 static bool load_obj(const std::string& obj_path, const std::string& mtl_arg, ObjData* out, std::string* err) {
   std::ifstream in(obj_path.c_str());
   if (!in) { *err = "cannot open OBJ file '" + obj_path + "': " + strerror(errno); return false; }
@@ -322,7 +410,13 @@ static bool load_obj(const std::string& obj_path, const std::string& mtl_arg, Ob
   std::map<std::string, int> mat_map;
   int material = -1;
   struct Face { std::vector<int> vi; int mat; };
-  std::vector<Face> faces;
+  std::vector<Face> faces;   // the current face group; triangulated when the group is flushed
+  // exportGroupsToShape runs at `g`, `o`, a usemtl that changes the material, and end of file
+  // (tiny_obj_loader.h:738-748, 806-818): range checks see the vertex array as of that moment
+  auto flush_faces = [&]() {
+    for (size_t i = 0; i < faces.size(); i++) triangulate_face(faces[i].vi, faces[i].mat, out->v, out);
+    faces.clear();
+  };
   std::string line;
   bool mtl_consumed = false;
   while (std::getline(in, line)) {
@@ -364,9 +458,12 @@ static bool load_obj(const std::string& obj_path, const std::string& mtl_arg, Ob
       tok += strspn(tok, " \t");
       std::string name(tok, strcspn(tok, " \t\r"));
       std::map<std::string, int>::const_iterator it = mat_map.find(name);
-      material = (it != mat_map.end()) ? it->second : -1;
+      const int next = (it != mat_map.end()) ? it->second : -1;
+      if (next != material) flush_faces();
+      material = next;
       continue;
     }
+    if ((tok[0] == 'g' || tok[0] == 'o') && is_space(tok[1])) { flush_faces(); continue; }
     if (0 == strncmp(tok, "mtllib", 6) && is_space(tok[6])) {
       // The reference ignores the file name and reads the MTL stream it was given
       // (MaterialStreamReader, material.h:784-809; scene_basics.h:224-225).
@@ -377,46 +474,10 @@ static bool load_obj(const std::string& obj_path, const std::string& mtl_arg, Ob
       }
       continue;
     }
-    // g / o / s / vt: no effect on triangle order or materials (shapes are concatenated in
-    // file order by scene_basics.h:270-286)
+    // s / vt: no effect on triangle order or materials (shapes are concatenated in file order by
+    // scene_basics.h:270-286)
   }
-  // triangulate (tiny_obj_loader.h:204-308 for quads).  The quad rule: compare the squared
-  // diagonals |v2-v0|^2 < |v3-v1|^2 -> [0,1,2],[0,2,3] else [0,1,3],[1,2,3]  (plain float ops,
-  // left-to-right sums, no fma: host code of the reference is compiled by the host compiler).
-  const std::vector<float>& v = out->v;
-  for (size_t i = 0; i < faces.size(); i++) {
-    const Face& f = faces[i];
-    size_t n = f.vi.size();
-    if (n < 3) continue;
-    if (n == 3) {
-      out->face_v.insert(out->face_v.end(), {f.vi[0], f.vi[1], f.vi[2]});
-      out->face_mat.push_back(f.mat);
-    } else if (n == 4) {
-      bool ok = true;
-      for (int k = 0; k < 4; k++) ok = ok && ((size_t)(3 * f.vi[k] + 2) < v.size()) && f.vi[k] >= 0;
-      if (!ok) continue;
-      const float* p0 = &v[3 * f.vi[0]]; const float* p1 = &v[3 * f.vi[1]];
-      const float* p2 = &v[3 * f.vi[2]]; const float* p3 = &v[3 * f.vi[3]];
-      float e02x = p2[0] - p0[0], e02y = p2[1] - p0[1], e02z = p2[2] - p0[2];
-      float e13x = p3[0] - p1[0], e13y = p3[1] - p1[1], e13z = p3[2] - p1[2];
-      float sqr02 = e02x * e02x + e02y * e02y + e02z * e02z;
-      float sqr13 = e13x * e13x + e13y * e13y + e13z * e13z;
-      if (sqr02 < sqr13) {
-        out->face_v.insert(out->face_v.end(), {f.vi[0], f.vi[1], f.vi[2], f.vi[0], f.vi[2], f.vi[3]});
-      } else {
-        out->face_v.insert(out->face_v.end(), {f.vi[0], f.vi[1], f.vi[3], f.vi[1], f.vi[2], f.vi[3]});
-      }
-      out->face_mat.push_back(f.mat);
-      out->face_mat.push_back(f.mat);
-    } else {
-      // n-gons (> 4): the reference ear-clips (tiny_obj_loader.h:310-564); no shipped asset has
-      // one.  DEVIATION: fan triangulation.
-      for (size_t k = 1; k + 1 < n; k++) {
-        out->face_v.insert(out->face_v.end(), {f.vi[0], f.vi[k], f.vi[k + 1]});
-        out->face_mat.push_back(f.mat);
-      }
-    }
-  }
+  flush_faces();
   return true;
 }
 

@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import ASSETS, ROOT, scene_objects
+from conftest import ASSETS, GOLDEN, ROOT, scene_objects
 
 
 def _host_scene(ipt, objects, **kw):
@@ -48,6 +48,26 @@ def test_loader_tables_bit_identical_to_oracle(ipt, oracle, name):
         assert a[k].tobytes() == b[k].tobytes(), k
     assert np.array_equal(g.camera(), o.camera())
     assert np.array_equal(g.get_materials(), o.get_materials())
+
+
+def _fuzz_cases():
+    path = os.path.join(GOLDEN, "loader_fuzz.npz")
+    return [str(c) for c in np.load(path)["cases"]] if os.path.exists(path) else []
+
+
+@pytest.mark.parametrize("case", _fuzz_cases())
+def test_loader_fuzz_product_against_reference_tables(ipt, oracle, case):
+    """the product's own OBJ/MTL parser on the fuzz files (tools/make_loader_fuzz.py): equal to the tables the
+    reference's loader produced, and bit-identical to the oracle's table in every field"""
+    from test_oracle import check_fuzz_tables, fuzz_objects
+    z = np.load(os.path.join(GOLDEN, "loader_fuzz.npz"))
+    g = _host_scene(ipt, fuzz_objects(case))
+    check_fuzz_tables(g.triangle_table(), g.nT, z[case + "_V"], z[case + "_N"], z[case + "_F"], z[case + "_M"])
+    o = oracle.OracleScene(fuzz_objects(case), ASSETS)
+    a, b = g.triangle_table(), o.triangle_table()
+    assert (g.nT, g.nE) == (o.nT, o.nE)
+    for k in a:
+        assert a[k].tobytes() == b[k].tobytes(), k
 
 
 def test_set_get_materials_roundtrip_and_handle_validation(ipt):
