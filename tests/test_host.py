@@ -221,3 +221,40 @@ def test_graph_compress_matches_oracle_compress(ipt, oracle):
     target = np.random.RandomState(1).randint(0, 256, (24, 24, 3)).astype(np.uint8)
     raw, data, _ = sc.create_graph(oracle.make_params(24, 24, 4, seed=3), target, threads=4)
     assert native.graph_compress(raw, sc.nT).tobytes() == data.tobytes()
+
+
+def test_gcn_consumer_matches_edge_list_message_passing():
+    """inverse_path_tracer_b200/gcn.py restates the reference's DGL network (ipt.py:28-84) with a dense weight matrix:
+    the dense message pass must equal the explicit per-edge sum, graph construction must follow ipt.py:67-82
+    (threshold, row normalisation, eye row -> node inputs), and a short fit must reduce the loss."""
+    import torch
+    from inverse_path_tracer_b200 import gcn
+    rng = np.random.RandomState(0)
+    nT = 12
+    w = rng.uniform(0, 1, (nT + 1, nT)) * (rng.uniform(0, 1, (nT + 1, nT)) < 0.4)
+    w[3] = 5e-4                       # a row entirely under P_MIN stays zero after thresholding
+    pixel = rng.uniform(0, 1, (nT + 1, nT, 3))
+    labels = rng.uniform(0, 1, (nT, 3))
+    W, x = gcn.build_graph(w, pixel, None)
+    assert W.shape == (nT, nT) and x.shape == (nT, 3)
+    assert torch.equal(x, torch.tensor(pixel[-1], dtype=torch.float32))
+    assert float(W[3].abs().sum()) == 0.0
+    rows = W.sum(-1)
+    assert all(abs(float(r) - 1.0) < 1e-6 or float(r) == 0.0 for r in rows)
+    torch.manual_seed(0)
+    layer = gcn.MPL(5, 7, None)
+    h = torch.randn(nT, 5)
+    dst, src = np.nonzero(W.numpy())
+    reduced = torch.zeros(nT, 5)
+    for d, s_ in zip(dst, src):       # DGL: msg = h[src] * w(edge), summed at dst; self loops carry weight 0
+        reduced[d] += h[s_] * W[d, s_]
+    want = layer.linear(torch.cat((h, reduced), -1))
+    assert torch.allclose(layer(W, h), want, atol=1e-6)
+    model = gcn.GCN(3, 3)
+    out1 = model(W, x)
+    outb = model(torch.stack([W, W]), torch.stack([x, x]))
+    assert out1.shape == (nT, 3) and torch.allclose(outb[0], out1, atol=1e-6) and float(out1.min()) > 0 and float(out1.max()) < 1
+    data = [(w, pixel, None, labels)]
+    _, l_short = gcn.fit(data, epochs=1, lr=1e-2, device="cpu")
+    _, l_long = gcn.fit(data, epochs=150, lr=1e-2, device="cpu")
+    assert l_long < 0.7 * l_short
