@@ -149,6 +149,13 @@ int iptPathKernelTimes(void* scene, float* ms, int max_count);
  * counter block (graph / grad passes, or render calls given no counter buffer); synchronous */
 int iptLastCounters(void* scene, unsigned long long* counters);
 
+/* Measurement aid for the traversal roofline (SURVEY.md section 8d asks for an L2-resident copy figure, which
+ * MEASURED_PEAKS.json does not hold): copies `bytes` (rounded down to 16) from one device buffer to another
+ * `reps` times with a grid of SMs x 8 blocks of 256 threads (128-bit loads and stores) and returns the
+ * read + write rate of the timed repetitions in GB/s, or a negative value on error.  Buffers that fit the
+ * L2 together measure the L2; larger ones HBM.  Synchronous; uses the device selected by iptSetDevice. */
+double iptMeasureCopyGBps(long long bytes, int reps);
+
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 unsigned long long iptKernelLaunchCount(void);
 

@@ -466,6 +466,36 @@ int iptSetTraversalMode(int mode) {
   g_traversal_mode = mode;
   return 0;
 }
+double iptMeasureCopyGBps(long long bytes, int reps) {
+  if (bytes < 16 || reps < 1) { fail("iptMeasureCopyGBps: bytes >= 16 and reps >= 1 required"); return -1.0; }
+  const int dev = g_device >= 0 ? g_device : 0;
+  if (cudaSetDevice(dev) != cudaSuccess) { fail("iptMeasureCopyGBps: no CUDA device"); return -1.0; }
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t n = (size_t)bytes / 16;
+  float4 *a = nullptr, *b = nullptr;
+  if (cudaMalloc(&a, n * 16) != cudaSuccess || cudaMalloc(&b, n * 16) != cudaSuccess) {
+    cudaFree(a);
+    fail("iptMeasureCopyGBps: allocation failed");
+    return -1.0;
+  }
+  cudaMemset(a, 0, n * 16);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; i++) launch_copy16(a, b, n, sms, nullptr);
+  cudaEventRecord(e0, nullptr);
+  for (int i = 0; i < reps; i++) launch_copy16(a, b, n, sms, nullptr);
+  cudaEventRecord(e1, nullptr);
+  const cudaError_t err = cudaEventSynchronize(e1);
+  float ms = 0.0f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  g_launches += (unsigned long long)reps + 3;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(a); cudaFree(b);
+  if (err != cudaSuccess || !(ms > 0.0f)) { fail(std::string("iptMeasureCopyGBps: ") + cudaGetErrorString(err)); return -1.0; }
+  return 2.0 * (double)(n * 16) * reps / (ms * 1e-3) / 1e9;
+}
+
 unsigned long long iptKernelLaunchCount(void) { return g_launches.load() + bvh_kernel_launches(); }
 int iptSetBvhBuilder(int mode) {
   if (mode < 0 || mode > 2) return fail("BVH builder mode must be 0 (auto), 1 (host) or 2 (GPU)");

@@ -23,6 +23,7 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
 cudaError_t launch_trace_rays(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter, int sm_count, cudaStream_t st);
 cudaError_t launch_trace_rays_stats(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter,
                                     unsigned long long* stats, int sm_count, cudaStream_t st);
+cudaError_t launch_copy16(const float4* src, float4* dst, size_t n, int sm_count, cudaStream_t st);
 cudaError_t launch_resolve(const float* partial, int n_pix, int groups, float* img, unsigned char* img8, cudaStream_t st);
 cudaError_t launch_loss_dldpx(const float* img, const unsigned char* target, int row_begin, int row_step, int width, int n_pix, double inv_n, float inv_spp,
                               float* dldpx, double* loss, cudaStream_t st);

@@ -32,7 +32,7 @@ EXPORTS = ["loadScene", "freeScene", "createImage", "createGraph", "getMaterials
            "iptRender", "iptRenderDevice", "iptCreateImageEx", "iptCreateGraphEx", "iptGraphAccumulateDevice",
            "iptGraphCompress", "iptRenderGrad", "iptRenderGradDevice", "iptSetMaterialsDevice", "iptBuildBVH",
            "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder", "iptTraceRaysStatsDevice",
-           "iptSetIntegrator"]
+           "iptSetIntegrator", "iptMeasureCopyGBps"]
 
 
 def lib():
@@ -44,6 +44,8 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.iptGetLastError.restype = C.c_char_p
         L.iptKernelLaunchCount.restype = C.c_ulonglong
+        L.iptMeasureCopyGBps.restype = C.c_double
+        L.iptMeasureCopyGBps.argtypes = [C.c_longlong, C.c_int]
         L.loadScene.restype = C.c_int
         vp = C.c_void_p
         L.freeScene.argtypes = [vp]
@@ -101,6 +103,14 @@ def default_params(**kw):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def measure_copy_gbps(nbytes, reps=20):
+    """read + write GB/s of a device-to-device copy of nbytes (L2-resident when 2 * nbytes fits the L2)"""
+    v = lib().iptMeasureCopyGBps(int(nbytes), int(reps))
+    if v < 0:
+        raise RuntimeError("iptMeasureCopyGBps failed: " + last_error())
+    return v
 
 
 def set_integrator(mode=0, wavefront_slots=0):

@@ -155,6 +155,9 @@ def bvh_and_render(a, sc, L):
 
 
 def trace_test(a, sc, L):
+    for mb in (16, 32, 48, 2048):
+        print("device copy of %4d MiB (read + write): %.0f GB/s%s" % (mb, native.measure_copy_gbps(mb << 20, 20 if mb < 1024 else 5),
+                                                                  "  <- source + destination fit the 126 MB L2" if 2 * mb <= 120 else ""))
     # incoherent rays only: random origins inside the room, random directions
     rng = np.random.RandomState(0)
     n = 8_000_000
