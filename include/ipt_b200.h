@@ -132,6 +132,14 @@ int iptBuildBVH(const float* boxes, const float* pos, int n, int leaf_size, floa
  * on, one host thread below), 1 = host, 2 = CUDA kernels.  All produce bit-identical trees. */
 int iptSetBvhBuilder(int mode);
 
+/* BVH scenes keep their few LARGE triangles (box diagonal > 1/4 of the scene's; room walls around a dense mesh)
+ * out of the tree and test them brute force from shared memory before each traversal: the tree stays tight and
+ * the traversal starts with a bound.  `max_count` caps that set (default 128, 0 = every triangle goes into the
+ * tree).  Applies to scenes loaded afterwards; results do not depend on it.  iptSceneLargeTriangles returns the
+ * size of the set for a loaded scene (0 for brute-force scenes), or -1. */
+int iptSetBvhLargeTriangleLimit(int max_count);
+int iptSceneLargeTriangles(void* scene);
+
 /* forward integrator for scenes traversed through the BVH: 0 = auto (wavefront), 1 = persistent megakernel
  * (the one brute-force scenes always use), 2 = wavefront: path state in device memory, one closest-hit
  * kernel per bounce over the compacted live paths.  `wavefront_slots` bounds the paths in flight per batch

@@ -8,4 +8,4 @@ Layout:
   ipt_cuda.py  host-side mirror of the reference's ipt_cuda.py entry points
   torch_api.py  torch tensors / autograd.Function over the device-pointer entry points
 """
-from .native import IptRenderParams, Scene, default_params, lib, library_path, set_integrator  # noqa: F401
+from .native import IptRenderParams, Scene, default_params, lib, library_path, set_bvh_large_triangle_limit, set_integrator  # noqa: F401

@@ -6,6 +6,7 @@
 // (libpt.so / libipt.so are the same file) validate what they are given.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -37,6 +38,8 @@ static std::mutex g_registry_mutex;
 static std::set<void*> g_registry;
 
 constexpr int kBruteForceMaxTris = 128;
+constexpr double kBigTriangleDiag = 0.25;   // a triangle is "large" when its box diagonal exceeds this fraction of the scene's
+static int g_big_max = 128;                 // at most this many large triangles leave the tree (0: none)
 
 static int fail(const std::string& msg) {
   g_error = msg;
@@ -84,6 +87,7 @@ struct SceneHandle {
   int bvh_depth = 1;
   int* bvh_prims = nullptr;
   int n_nodes = 0;
+  int n_big = 0;
   bool use_bvh = false;
   bool host_only = false;
   // ring of CUDA event pairs bracketing the last kEventRing k_paths launches (roofline timing without
@@ -99,7 +103,7 @@ struct SceneHandle {
   DevScene dev() const {
     DevScene d;
     d.geom = geom; d.planes = planes; d.grange = grange; d.slot_edges = slot_edges; d.slot_tri = slot_tri; d.nGroups = n_groups; d.nSlots = n_slots; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
-    d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.use_bvh = use_bvh ? 1 : 0; d.plain = (!host.any_vn && !host.any_specular) ? 1 : 0;
+    d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.nBig = n_big; d.use_bvh = use_bvh ? 1 : 0; d.plain = (!host.any_vn && !host.any_specular) ? 1 : 0;
     memcpy(d.cam, host.cam, sizeof(d.cam));
     return d;
   }
@@ -161,11 +165,12 @@ static void pack_materials(const HostScene& hs, std::vector<float4>* mat) {
 static bool edges_negated(const float* ea, const float* eb) {
   return ea[0] == -eb[0] && ea[1] == -eb[1] && ea[2] == -eb[2] && ea[3] == -eb[3];
 }
-static void build_plane_groups(const HostScene& hs, std::vector<float4>* planes, std::vector<int2>* grange,
+// `subset`: ascending triangle ids to group (all triangles of a brute-force scene, the large ones of a BVH scene)
+static void build_plane_groups(const HostScene& hs, const std::vector<int>& subset, std::vector<float4>* planes, std::vector<int2>* grange,
                                std::vector<float4>* edges, std::vector<int2>* slot_ids) {
-  const size_t nT = hs.tris.size();
   std::vector<std::vector<int>> members;
-  for (size_t i = 0; i < nT; i++) {
+  for (size_t si = 0; si < subset.size(); si++) {
+    const int i = subset[si];
     const HostTriangle& t = hs.tris[i];
     int g = -1;
     for (size_t k = 0; k < members.size(); k++) {
@@ -175,7 +180,7 @@ static void build_plane_groups(const HostScene& hs, std::vector<float4>* planes,
       if (r.n[0] == t.n[0] && r.n[1] == t.n[1] && r.n[2] == t.n[2] && r.plane_k == t.plane_k) { g = (int)k; break; }
     }
     if (g < 0) { g = (int)members.size(); members.push_back(std::vector<int>()); }
-    members[g].push_back((int)i);
+    members[g].push_back(i);
   }
   planes->clear(); grange->clear(); edges->clear(); slot_ids->clear();
   auto push_edge = [&](const float* e) { edges->push_back(make_float4(e[0], e[1], e[2], e[3])); };
@@ -255,10 +260,42 @@ static int upload_scene(SceneHandle* h) {
   IPT_CUDA(cudaMemcpy(h->light, light.data(), light.size() * sizeof(float4), cudaMemcpyHostToDevice));
 
   h->use_bvh = (g_traversal_mode == 2) || (g_traversal_mode == 0 && (int)nT > kBruteForceMaxTris);
-  if (!h->use_bvh && nT) {
+  // the brute-force set: every triangle of a small scene; in a BVH scene the few triangles that are large against
+  // the scene (room walls around a dense mesh).  Left in the tree, a large triangle inflates the boxes of every
+  // node above its leaf and rays far from the mesh descend deep for nothing; outside it the tree stays tight and
+  // the set doubles as an early bound (its hit is found before the traversal starts).  Only automatic BVH scenes
+  // do this: a scene forced into BVH mode (iptSetTraversalMode(2)) keeps every triangle in the tree.
+  std::vector<int> brute, rest;
+  if (!h->use_bvh) {
+    for (size_t i = 0; i < nT; i++) brute.push_back((int)i);
+  } else if ((int)nT > kBruteForceMaxTris && g_big_max > 0) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t i = 0; i < nT; i++)
+      for (int j = 0; j < 3; j++)
+        for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], hs.tris[i].v[j][k]); hi[k] = fmaxf(hi[k], hs.tris[i].v[j][k]); }
+    const double scene_diag2 = (double)(hi[0] - lo[0]) * (hi[0] - lo[0]) + (double)(hi[1] - lo[1]) * (hi[1] - lo[1]) + (double)(hi[2] - lo[2]) * (hi[2] - lo[2]);
+    std::vector<std::pair<double, int>> cand;
+    for (size_t i = 0; i < nT; i++) {
+      const HostTriangle& t = hs.tris[i];
+      double d2 = 0.0;
+      for (int k = 0; k < 3; k++) {
+        const double e = (double)fmaxf(fmaxf(t.v[0][k], t.v[1][k]), t.v[2][k]) - (double)fminf(fminf(t.v[0][k], t.v[1][k]), t.v[2][k]);
+        d2 += e * e;
+      }
+      if (d2 > kBigTriangleDiag * kBigTriangleDiag * scene_diag2) cand.push_back(std::make_pair(-d2, (int)i));
+    }
+    std::sort(cand.begin(), cand.end());
+    if ((int)cand.size() > g_big_max) cand.resize(g_big_max);
+    std::vector<char> is_big(nT, 0);
+    for (size_t c = 0; c < cand.size(); c++) is_big[cand[c].second] = 1;
+    for (size_t i = 0; i < nT; i++) (is_big[i] ? brute : rest).push_back((int)i);
+  }
+  if (h->use_bvh && rest.empty() && brute.empty()) for (size_t i = 0; i < nT; i++) rest.push_back((int)i);
+  h->n_big = h->use_bvh ? (int)brute.size() : 0;
+  if (!brute.empty()) {
     std::vector<float4> planes, edges;
     std::vector<int2> grange, slot_tri;
-    build_plane_groups(hs, &planes, &grange, &edges, &slot_tri);
+    build_plane_groups(hs, brute, &planes, &grange, &edges, &slot_tri);
     h->n_groups = (int)planes.size();
     h->n_slots = (int)slot_tri.size();
     IPT_CUDA(cudaMalloc(&h->planes, planes.size() * sizeof(float4)));
@@ -273,9 +310,10 @@ static int upload_scene(SceneHandle* h) {
   if (h->use_bvh && nT) {
     // triangle-level tree: box = vertex bounds, split position = triangle center (the analogue of
     // Object::getBBox / getPosition, scene_basics.h:417-424, with triangles as primitives)
-    std::vector<float> boxes(6 * nT), pos(3 * nT);
-    for (size_t i = 0; i < nT; i++) {
-      const HostTriangle& t = hs.tris[i];
+    const size_t nR = rest.size();
+    std::vector<float> boxes(6 * nR), pos(3 * nR);
+    for (size_t i = 0; i < nR; i++) {
+      const HostTriangle& t = hs.tris[rest[i]];
       for (int k = 0; k < 3; k++) {
         boxes[6 * i + k] = fminf(fminf(t.v[0][k], t.v[1][k]), t.v[2][k]);
         boxes[6 * i + 3 + k] = fmaxf(fmaxf(t.v[0][k], t.v[1][k]), t.v[2][k]);
@@ -285,7 +323,8 @@ static int upload_scene(SceneHandle* h) {
     std::vector<BvhNodeHost> nodes;
     std::vector<int> perm;
     std::string err;
-    if (!build_bvh(boxes.data(), pos.data(), (int)nT, 4, &nodes, &perm, h->device, &err)) return fail("BVH build failed: " + err);
+    if (nR && !build_bvh(boxes.data(), pos.data(), (int)nR, 4, &nodes, &perm, h->device, &err)) return fail("BVH build failed: " + err);
+    for (size_t j = 0; j < perm.size(); j++) perm[j] = rest[perm[j]];   // tree order -> triangle ids
     std::vector<float4> packed(2 * nodes.size());
     for (size_t i = 0; i < nodes.size(); i++) {
       int ro = nodes[i].rightOffset;
@@ -330,20 +369,22 @@ static int upload_scene(SceneHandle* h) {
       wide[4 * i + 3] = make_float4(packed[2 * r + 1].x, packed[2 * r + 1].y, packed[2 * r + 1].z, 0.0f);
     }
     if (max_depth > 64) return fail("BVH deeper than 64 levels: the traversal stack (like the reference's todo[64], bvh.h:43) cannot hold it");
-    h->bvh_root_desc = desc_of(0);
+    h->bvh_root_desc = nodes.empty() ? 0 : desc_of(0);
     h->bvh_depth = max_depth;
     h->n_nodes = (int)nodes.size();
-    IPT_CUDA(cudaMalloc(&h->bvh_wide, wide.size() * sizeof(float4)));
-    IPT_CUDA(cudaMemcpy(h->bvh_wide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    IPT_CUDA(cudaMalloc(&h->bvh_nodes, packed.size() * sizeof(float4)));
-    IPT_CUDA(cudaMalloc(&h->bvh_prims, perm.size() * sizeof(int)));
-    IPT_CUDA(cudaMemcpy(h->bvh_nodes, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    IPT_CUDA(cudaMemcpy(h->bvh_prims, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
-    // leaf triangles are read in tree order: store their records that way (slot j = triangle perm[j]), so a leaf is
-    // one contiguous run and the id lookup is only needed for accepted hits
-    std::vector<float4> leaf_geom(4 * nT);
-    for (size_t j = 0; j < nT; j++) memcpy(&leaf_geom[4 * j], &geom[4 * (size_t)perm[j]], 4 * sizeof(float4));
-    IPT_CUDA(cudaMemcpy(h->geom, leaf_geom.data(), leaf_geom.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    IPT_CUDA(cudaMalloc(&h->bvh_wide, std::max<size_t>(wide.size(), 4) * sizeof(float4)));
+    IPT_CUDA(cudaMalloc(&h->bvh_nodes, std::max<size_t>(packed.size(), 2) * sizeof(float4)));
+    IPT_CUDA(cudaMalloc(&h->bvh_prims, std::max<size_t>(perm.size(), 1) * sizeof(int)));
+    if (!nodes.empty()) {
+      IPT_CUDA(cudaMemcpy(h->bvh_wide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice));
+      IPT_CUDA(cudaMemcpy(h->bvh_nodes, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice));
+      IPT_CUDA(cudaMemcpy(h->bvh_prims, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
+      // leaf triangles are read in tree order: store their records that way (slot j = triangle perm[j]), so a leaf is
+      // one contiguous run and the id lookup is only needed for accepted hits
+      std::vector<float4> leaf_geom(4 * perm.size());
+      for (size_t j = 0; j < perm.size(); j++) memcpy(&leaf_geom[4 * j], &geom[4 * (size_t)perm[j]], 4 * sizeof(float4));
+      IPT_CUDA(cudaMemcpy(h->geom, leaf_geom.data(), leaf_geom.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
   }
   return 0;
 }
@@ -454,6 +495,15 @@ void iptDefaultParams(IptRenderParams* p) {
 
 int iptSetAssetRoot(const char* root) { g_asset_root = root ? root : ""; return 0; }
 int iptSetDevice(int device) { g_device = device; return 0; }
+int iptSetBvhLargeTriangleLimit(int max_count) {
+  if (max_count < 0 || max_count > kBruteForceMaxTris) return fail("large-triangle limit must be in [0, 128]");
+  g_big_max = max_count;
+  return 0;
+}
+int iptSceneLargeTriangles(void* scene) {
+  SceneHandle* h = checked(scene);
+  return h ? h->n_big : -1;
+}
 int iptSetIntegrator(int mode, int wavefront_slots) {
   if (mode < 0 || mode > 2) return fail("integrator must be 0, 1 or 2");
   if (wavefront_slots < 0) return fail("wavefront_slots must be >= 0");

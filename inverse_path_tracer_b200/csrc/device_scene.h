@@ -42,6 +42,7 @@ struct DevScene {
   int bvh_depth;             // levels of the tree = entries of the per-thread traversal stack (<= 64)
   const int* bvh_prims;      // triangle index per BVH slot
   int nT, nE, nNodes;
+  int nBig;                  // BVH scenes: triangles kept out of the tree and tested brute force (planes / slot_* describe them)
   int use_bvh;
   int plain;                 // no per-vertex normals and no specular lobe anywhere in the scene
   float cam[16];

@@ -32,7 +32,8 @@ EXPORTS = ["loadScene", "freeScene", "createImage", "createGraph", "getMaterials
            "iptRender", "iptRenderDevice", "iptCreateImageEx", "iptCreateGraphEx", "iptGraphAccumulateDevice",
            "iptGraphCompress", "iptRenderGrad", "iptRenderGradDevice", "iptSetMaterialsDevice", "iptBuildBVH",
            "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder", "iptTraceRaysStatsDevice",
-           "iptSetIntegrator", "iptMeasureCopyGBps"]
+           "iptSetIntegrator", "iptMeasureCopyGBps",
+           "iptSetBvhLargeTriangleLimit", "iptSceneLargeTriangles"]
 
 
 def lib():
@@ -113,6 +114,12 @@ def measure_copy_gbps(nbytes, reps=20):
     return v
 
 
+def set_bvh_large_triangle_limit(max_count=128):
+    """cap of the brute-force set of large triangles in BVH scenes loaded afterwards (0: all triangles in the tree)"""
+    if lib().iptSetBvhLargeTriangleLimit(int(max_count)) != 0:
+        raise ValueError(last_error())
+
+
 def set_integrator(mode=0, wavefront_slots=0):
     """Forward integrator for BVH scenes: 0 auto (wavefront), 1 persistent megakernel, 2 wavefront;
     wavefront_slots bounds the paths in flight per batch (0 = default)."""
@@ -169,6 +176,8 @@ class Scene:
         ip = [C.cast(C.byref(info, 4 * i), C.c_void_p) for i in range(5)]
         _check(L.iptSceneInfo(self.h, *ip), "iptSceneInfo")
         self.nT, self.nE, self.nO, self.n_nodes, self.uses_bvh = [int(x) for x in info]
+        L.iptSceneLargeTriangles.argtypes = [C.c_void_p]
+        self.n_large = int(L.iptSceneLargeTriangles(self.h))   # BVH scenes: triangles kept out of the tree
 
     @classmethod
     def from_file(cls, scenefile, asset_root=None, **kw):

@@ -140,6 +140,35 @@ def test_wavefront_integrator_bit_exact(ipt, oracle, scene, w, h, spp, depth, gs
     assert img_s.tobytes() == img_o[1::3].tobytes()
 
 
+def test_large_triangle_set_does_not_change_results(ipt, oracle):
+    """BVH scenes keep their large triangles (here the 18 Cornell walls around the 1280-triangle sphere) out of the
+    tree and test them brute force first; hits and images must equal the oracle with the set on, capped and off"""
+    objects = scene_objects("cornell_sphere")
+    o = oracle.OracleScene(objects, ASSETS)
+    rays = np.concatenate([random_rays(20000, 5), adversarial_rays(o)])
+    tri_o, t_o = o.trace(rays)
+    po = oracle.make_params(40, 32, 6, max_depth=5, seed=4)
+    img_o, cnt_o = o.render(po)
+    sizes = []
+    try:
+        for limit in (128, 7, 0):
+            ipt.set_bvh_large_triangle_limit(limit)
+            g = ipt.Scene(objects, asset_root=ASSETS)
+            assert g.uses_bvh
+            sizes.append(g.n_large)
+            tri_g, t_g = g.trace(rays)
+            assert np.array_equal(tri_g, tri_o) and t_g.tobytes() == t_o.tobytes(), "limit %d" % limit
+            for integ in (1, 2):
+                ipt.set_integrator(integ, 0)
+                img_g, cnt_g = g.render(ipt.default_params(width=40, height=32, spp=6, max_depth=5, seed=4))
+                assert cnt_g == cnt_o and img_g.tobytes() == img_o.tobytes(), "limit %d integrator %d" % (limit, integ)
+            g.close()
+    finally:
+        ipt.set_bvh_large_triangle_limit(128)
+        ipt.set_integrator(0, 0)
+    assert sizes == [18, 7, 0]
+
+
 def test_row_sharding_and_determinism(ipt, oracle):
     g = ipt.Scene(_scene0(oracle), asset_root=ASSETS)
     p = ipt.default_params(width=96, height=80, spp=32, seed=3)

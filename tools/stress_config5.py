@@ -112,8 +112,8 @@ def main():
     t0 = time.time()
     sc = ipt.Scene(objects)
     t_load = time.time() - t0
-    print("loadScene: %.2f s total (OBJ parse + triangle setup + GPU BVH build + upload); nT=%d nE=%d nodes=%d bvh=%d; %d kernel launches" % (
-        t_load, sc.nT, sc.nE, sc.n_nodes, sc.uses_bvh, L.iptKernelLaunchCount() - k0))
+    print("loadScene: %.2f s total (OBJ parse + triangle setup + GPU BVH build + upload); nT=%d nE=%d nodes=%d bvh=%d large-triangle set=%d; %d kernel launches" % (
+        t_load, sc.nT, sc.nE, sc.n_nodes, sc.uses_bvh, sc.n_large, L.iptKernelLaunchCount() - k0))
     if a.only_render == 3:
         pass
     elif a.only_render:
