@@ -695,7 +695,7 @@ int iptTraceRaysDevice(void* scene, const float* rays_dev, int n, int* tri_dev, 
   IPT_CUDA(cudaSetDevice(h->device));
   IPT_CUDA(h->trace_counter.reserve(sizeof(unsigned long long)));
   IPT_CUDA(launch_trace_rays(h->dev(), rays_dev, n, tri_dev, t_dev, (unsigned long long*)h->trace_counter.ptr, h->sm_count, (cudaStream_t)stream));
-  g_launches += 1;
+  g_launches += (h->use_bvh && h->n_big > 0) ? 2 : 1;
   return 0;
 }
 
@@ -709,7 +709,7 @@ int iptTraceRaysStatsDevice(void* scene, const float* rays_dev, int n, int* tri_
   IPT_CUDA(h->trace_counter.reserve(sizeof(unsigned long long)));
   IPT_CUDA(launch_trace_rays_stats(h->dev(), rays_dev, n, tri_dev, t_dev, (unsigned long long*)h->trace_counter.ptr, stats_dev, h->sm_count,
                                    (cudaStream_t)stream));
-  g_launches += 1;
+  g_launches += (h->use_bvh && h->n_big > 0) ? 2 : 1;
   return 0;
 }
 
