@@ -20,8 +20,8 @@ LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libipt_b200.so")
 
-SOURCES = ["api.cu", "kernels.cu", "bvh_build.cu", "scene_host.cu", "png_io.cpp"]
-HEADERS = ["ipt_math.cuh", "device_scene.h", "kernels.h", "scene_host.h", os.path.join(ROOT, "include", "ipt_b200.h")]
+SOURCES = ["api.cu", "paths.cu", "trace.cu", "wavefront.cu", "bvh_build.cu", "scene_host.cu", "png_io.cpp"]
+HEADERS = ["ipt_math.cuh", "intersect.cuh", "shading.cuh", "device_scene.h", "kernels.h", "scene_host.h", os.path.join(ROOT, "include", "ipt_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]

@@ -442,7 +442,7 @@ static int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsi
   out.counters = counters_dev ? counters_dev : ctr;
   out.partial = (float*)h->partial.ptr;
   if (sc.use_bvh && g_integrator != 1) {
-    // large scenes: wavefront (kernels.cu); batches of at most `cap` paths
+    // large scenes: wavefront (wavefront.cu); batches of at most `cap` paths
     const long long total = (long long)rp.n_pix * std::min(rp.spp, rp.group_samples);
     const int cap = (int)std::max<long long>(1, std::min<long long>(total, (long long)g_wf_slots));
     IPT_CUDA(h->wavefront.reserve(wavefront_workspace_bytes(cap)));

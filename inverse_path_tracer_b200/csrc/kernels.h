@@ -1,4 +1,4 @@
-// kernels.h -- host-callable launchers implemented in kernels.cu / bvh_build.cu
+// kernels.h -- host-callable launchers implemented in paths.cu / trace.cu / wavefront.cu / bvh_build.cu
 #pragma once
 #include <cuda_runtime.h>
 
@@ -20,6 +20,9 @@ cudaError_t launch_paths(int mode, const DevScene& sc, const DevRender& rp, cons
 size_t wavefront_workspace_bytes(int cap);
 cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* workspace, int cap, float* partial, unsigned long long* counters,
                              int sm_count, int* host_live, unsigned long long* n_launches, cudaStream_t st);
+// one bounce of the wavefront integrator (trace.cu): closest hits of the rays [0, n) u [cap, cap + n), n = *n_live
+cudaError_t launch_trace_bounce(const DevScene& sc, const float* rays, const int* n_live, int cap, int* tri, float* t, unsigned long long* counter,
+                                int sm_count, unsigned long long* n_launches, cudaStream_t st);
 cudaError_t launch_trace_rays(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter, int sm_count, cudaStream_t st);
 cudaError_t launch_trace_rays_stats(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter,
                                     unsigned long long* stats, int sm_count, cudaStream_t st);

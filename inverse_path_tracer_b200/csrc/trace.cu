@@ -1,0 +1,214 @@
+// trace.cu -- closest hit for ray batches (Scene::getIntersection, scene.h:127 -> bvh.h:37-107 ->
+// scene_basics.h:426-459): iptTraceRays* and the per-bounce traversal of the wavefront integrator.
+//
+//   k_trace_rays       brute force over the scene's shared-memory set (whole small scene / large triangles of a BVH scene)
+//   k_trace_rays_bvh   persistent, phased BVH traversal
+//   k_copy16           copy-bandwidth measurement aid (iptMeasureCopyGBps)
+#include <algorithm>
+
+#include "intersect.cuh"
+#include "kernels.h"
+
+namespace ipt {
+
+// Persistent ray-batch traversal.  Each lane owns one ray at a time and is a state machine (inner node /
+// leaf / finished); the warp advances in three phases so that lanes in the same state execute together:
+//   fetch  -- every finished lane stores its hit and claims the next ray (one atomic per warp),
+//   inner  -- lanes at inner nodes keep descending while at least kInnerQuorum of them are (a lane that
+//             reaches a leaf, or finishes, waits),
+//   leaf   -- every lane holding a leaf tests its triangles, then pops.
+// (One state machine step per lane per trip -- the previous form -- executes the union of all three bodies on
+// every trip with ~9 of 32 lanes active in each.)
+// Ray index space: `n_live == nullptr`: rays [0, n).  Otherwise (wavefront): n = *n_live and the batch is
+// [0, n) u [cap, cap + n).  A ray with direction 0 is "no ray": a miss.
+#ifndef IPT_INNER_QUORUM
+#define IPT_INNER_QUORUM 10
+#endif
+constexpr int kInnerQuorum = IPT_INNER_QUORUM;
+#ifndef IPT_FETCH_QUORUM
+#define IPT_FETCH_QUORUM 8
+#endif
+constexpr int kFetchQuorum = IPT_FETCH_QUORUM;
+
+template <bool STATS>
+__global__ void __launch_bounds__(kBlock) k_trace_rays_bvh(DevScene sc, const float* __restrict__ rays, int n_direct, const int* __restrict__ n_live, int cap,
+                                                           int* __restrict__ tri, float* __restrict__ tout, unsigned long long* __restrict__ counter,
+                                                           unsigned long long* __restrict__ stats) {
+  extern __shared__ float4 smem[];
+  int* col = reinterpret_cast<int*>(smem) + threadIdx.x;
+  const int stride = blockDim.x;
+  const unsigned lane = threadIdx.x & 31u;
+  // a scene with a brute-force set (large triangles kept out of the tree): k_trace_rays has already written each
+  // ray's hit among those into tri / tout; the traversal starts from that bound
+  const bool seeded = sc.nGroups > 0;
+  const long long n = n_live ? (long long)*n_live : (long long)n_direct;
+  const long long total = n_live ? 2 * n : n;
+  unsigned nodes = 0, tris = 0;
+  BvhRay r;
+  r.cur = kBvhDone;
+  r.best_t = INFINITY; r.best_i = -1; r.sp = 0;
+  long long idx = -1;
+  bool exhausted = false;       // the batch has no ray left for this lane
+  for (;;) {
+    // ---- fetch ----
+    const bool want = r.cur == kBvhDone && !exhausted;
+    const unsigned wm = __ballot_sync(kFull, want);
+    // a fetch costs the warp ~60 instructions however few lanes take part: wait for kFetchQuorum finished lanes unless
+    // the others have nothing to do either
+    if (wm && (__popc(wm) >= kFetchQuorum || __ballot_sync(kFull, r.cur != kBvhDone) == 0u)) {
+      if (want && idx >= 0) { tri[idx] = r.best_i; tout[idx] = r.best_t; idx = -1; }
+      const int leader = __ffs(wm) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(wm));
+      base = __shfl_sync(kFull, base, leader);
+      if (want) {
+        const long long mine = (long long)base + __popc(wm & ((1u << lane) - 1u));
+        if (mine >= total) {
+          exhausted = true;
+        } else {
+          idx = mine < n ? mine : (long long)cap + (mine - n);
+          const float2* r2 = reinterpret_cast<const float2*>(rays + 6 * idx);
+          const float2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2);
+          r.best_i = -1; r.best_t = INFINITY;
+          if (!(b.y == 0.0f && c.x == 0.0f && c.y == 0.0f)) {
+            const f3 rp = mk3(a.x, a.y, b.x), rd = mk3(b.y, c.x, c.y);
+            bvh_begin(sc, r, rp, rd);
+            if (seeded) { r.best_i = tri[idx]; r.best_t = tout[idx]; }
+          }
+        }
+      }
+    }
+    if (__all_sync(kFull, r.cur == kBvhDone)) {
+      if (__all_sync(kFull, exhausted)) break;
+      continue;   // lanes whose new ray ended at once (no ray / root box missed) store and refetch at the top
+    }
+    // ---- inner nodes ----
+    for (;;) {
+      const bool inner = (unsigned)r.cur < (unsigned)kBvhDone;
+      const unsigned im = __ballot_sync(kFull, inner);
+      if (im == 0u) break;
+      if (__popc(im) < kInnerQuorum) {
+        // leave only if the waiting lanes will then do something: a leaf to test, or enough finished lanes for a fetch
+        const unsigned leaves = __ballot_sync(kFull, r.cur < 0);
+        const unsigned idle = __ballot_sync(kFull, r.cur == kBvhDone && !exhausted);
+        if (leaves != 0u || __popc(idle) >= kFetchQuorum) break;
+      }
+      if (inner) bvh_step<STATS>(sc, r, col, stride, &nodes, &tris);
+    }
+    // ---- leaves ----
+    if (r.cur < 0) bvh_step<STATS>(sc, r, col, stride, &nodes, &tris);
+  }
+  if (idx >= 0) { tri[idx] = r.best_i; tout[idx] = r.best_t; }
+  if (STATS) {
+    atomicAdd(stats, (unsigned long long)nodes);
+    atomicAdd(stats + 1, (unsigned long long)tris);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// brute-force closest hit of a ray batch against the scene's shared-memory set: the whole scene of a small scene, or
+// the large-triangle set of a BVH scene (then k_trace_rays_bvh continues from these hits).  Index space as in
+// k_trace_rays_bvh: [0, n_direct), or with n_live the two halves [0, n) u [cap, cap + n) of a wavefront bounce.
+__global__ void __launch_bounds__(kBlock) k_trace_rays(DevScene sc, const float* __restrict__ rays, int n_direct, const int* __restrict__ n_live, int cap,
+                                                       int* __restrict__ tri, float* __restrict__ tout) {
+  extern __shared__ float4 smem[];
+  float4* after;
+  const SmallScene ss = stage_small_scene(sc, smem, &after);
+  __syncthreads();
+  const long long n = n_live ? (long long)*n_live : (long long)n_direct;
+  const long long total = n_live ? 2 * n : n;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
+    const long long i = m < n ? m : (long long)cap + (m - n);
+    const float2* r2 = reinterpret_cast<const float2*>(rays + 6 * i);
+    const float2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2);
+    f3 p = mk3(a.x, a.y, b.x), d = mk3(b.y, c.x, c.y);
+    HitRec h = closest_hit_small(ss, p, d);
+    tri[i] = h.tri;
+    tout[i] = h.t;
+  }
+}
+
+// dynamic shared memory of k_trace_rays_bvh: one stack column per thread
+static size_t trace_bvh_smem_bytes(const DevScene& sc) { return bvh_stack_bytes(sc); }
+
+// brute-force pass over the scene's shared-memory set (whole small scene / large-triangle set of a BVH scene)
+static cudaError_t launch_trace_small(const DevScene& sc, const float* rays, int n_direct, const int* n_live, int cap, int* tri, float* t, int sm_count,
+                                      cudaStream_t st) {
+  const size_t smem = small_scene_smem_bytes(sc.nSlots, sc.nGroups);
+  cudaError_t e = cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long want = n_live ? (long long)sm_count * 16 : ((long long)n_direct + kBlock - 1) / kBlock;
+  const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm_count * 16));
+  k_trace_rays<<<grid, kBlock, smem, st>>>(sc, rays, n_direct, n_live, cap, tri, t);
+  return cudaGetLastError();
+}
+
+// one bounce of the wavefront integrator: hits of the rays [0, n) u [cap, cap + n), n = *n_live
+cudaError_t launch_trace_bounce(const DevScene& sc, const float* rays, const int* n_live, int cap, int* tri, float* t, unsigned long long* counter,
+                                int sm_count, unsigned long long* n_launches, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  if (sc.nGroups > 0) {
+    e = launch_trace_small(sc, rays, 0, n_live, cap, tri, t, sm_count, st);
+    if (e != cudaSuccess) return e;
+    *n_launches += 1;
+  }
+  const size_t smem = trace_bvh_smem_bytes(sc);
+  e = cudaFuncSetAttribute(k_trace_rays_bvh<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int nb = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_rays_bvh<false>, kBlock, smem);
+  if (nb < 1) nb = 1;
+  k_trace_rays_bvh<false><<<sm_count * nb, kBlock, smem, st>>>(sc, rays, 0, n_live, cap, tri, t, counter, nullptr);
+  *n_launches += 1;
+  return cudaGetLastError();
+}
+
+// plain grid-stride copy, 16 bytes per thread per step (iptMeasureCopyGBps)
+__global__ void __launch_bounds__(256) k_copy16(const float4* __restrict__ src, float4* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+cudaError_t launch_copy16(const float4* src, float4* dst, size_t n, int sm_count, cudaStream_t st) {
+  k_copy16<<<sm_count * 8, 256, 0, st>>>(src, dst, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_trace_rays(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter, int sm_count, cudaStream_t st) {
+  if (sc.use_bvh) {
+    if (sc.nGroups > 0) {
+      cudaError_t e0 = launch_trace_small(sc, rays, n, nullptr, 0, tri, t, sm_count, st);
+      if (e0 != cudaSuccess) return e0;
+    }
+    const size_t smem = trace_bvh_smem_bytes(sc);
+    cudaError_t e = cudaFuncSetAttribute(k_trace_rays_bvh<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int nb = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_rays_bvh<false>, kBlock, smem);
+    if (nb < 1) nb = 1;
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    k_trace_rays_bvh<false><<<sm_count * nb, kBlock, smem, st>>>(sc, rays, n, nullptr, 0, tri, t, counter, nullptr);
+    return cudaGetLastError();
+  }
+  return launch_trace_small(sc, rays, n, nullptr, 0, tri, t, sm_count, st);
+}
+
+cudaError_t launch_trace_rays_stats(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter,
+                                    unsigned long long* stats, int sm_count, cudaStream_t st) {
+  const size_t smem = trace_bvh_smem_bytes(sc);
+  cudaError_t e = cudaFuncSetAttribute(k_trace_rays_bvh<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int nb = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_rays_bvh<true>, kBlock, smem);
+  if (nb < 1) nb = 1;
+  e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  if (sc.nGroups > 0) {
+    e = launch_trace_small(sc, rays, n, nullptr, 0, tri, t, sm_count, st);
+    if (e != cudaSuccess) return e;
+  }
+  k_trace_rays_bvh<true><<<sm_count * nb, kBlock, smem, st>>>(sc, rays, n, nullptr, 0, tri, t, counter, stats);
+  return cudaGetLastError();
+}
+
+}  // namespace ipt

@@ -1,0 +1,362 @@
+// wavefront.cu -- forward integrator for BVH scenes: path state in HBM, one traversal per bounce (trace.cu)
+#include <algorithm>
+
+#include "intersect.cuh"
+#include "kernels.h"
+#include "shading.cuh"
+
+namespace ipt {
+
+// ------------------------------------------------------------------------------------------------
+// Wavefront forward integrator for BVH scenes.
+//
+// k_paths keeps a whole path in registers, which is the right shape for scenes that fit shared memory, but
+// with a BVH the traversal then runs at the occupancy of a 96-register kernel and every warp mixes rays of
+// all bounce depths.  For large scenes the forward pass is split instead: one light traversal kernel
+// (k_trace_rays_bvh, the persistent traversal of the ray-batch entry point) between shading kernels that keep
+// the path state in HBM, compacted every bounce.  A batch is `tile_n` pixels x `ns` consecutive samples, all
+// at the same bounce; arithmetic per path and the order of every sum are those of k_paths, so the image is
+// bit-identical to the megakernel's and to the oracle's.
+//
+//   live slot j of a bounce:  state[k * cap + j], k = 0..5 (float4 each)
+//     S0 = {multiplier, path index in batch}   S1 = {prevMultiplier, flags}     S2 = {L, cos(theta) of the shadow ray}
+//     S3 = {L_e, p_t of the sampled light}      S4 = {L_d, sampled light id}     S5 = {BSDF(direct) of the bounce, -}
+//   rays[6 * j] extension ray, rays[6 * (cap + j)] shadow ray of the previous bounce (direction 0 = no ray)
+//   hits likewise at j and cap + j.
+// ------------------------------------------------------------------------------------------------
+enum { WF_END_AFTER = 1, WF_SH_VALID = 2, WF_EXT_VALID = 4 };
+constexpr int kWfBlock = 256;
+
+struct WfBatch {
+  int cap;          // slots per array
+  int tile_p0;      // first local pixel of the tile
+  int tile_n;       // pixels in the tile
+  int s0;           // first sample of the batch
+  int ns;           // samples per pixel in the batch
+};
+
+__device__ __forceinline__ void wf_path_ids(const DevRender& rp, const WfBatch& b, int path, int* pixel, int* sample, float* pix_c, float* pix_r) {
+  const int ss = path / b.tile_n;
+  const int pl = b.tile_p0 + (path - ss * b.tile_n);
+  const int lr = pl / rp.width;
+  const int c = pl - lr * rp.width;
+  const int r = rp.row_begin + lr * rp.row_step;
+  *pixel = r * rp.width + c;
+  *sample = b.s0 + ss;
+  *pix_c = (float)c;
+  *pix_r = (float)r;
+}
+
+__device__ __forceinline__ void wf_store_ray(float* __restrict__ rays, size_t idx, f3 p, f3 d) {
+  float2* r2 = reinterpret_cast<float2*>(rays + 6 * idx);
+  r2[0] = make_float2(p.x, p.y); r2[1] = make_float2(p.z, d.x); r2[2] = make_float2(d.y, d.z);
+}
+__device__ __forceinline__ void wf_load_ray(const float* __restrict__ rays, size_t idx, f3* p, f3* d) {
+  const float2* r2 = reinterpret_cast<const float2*>(rays + 6 * idx);
+  const float2 a = r2[0], b = r2[1], c = r2[2];
+  *p = mk3(a.x, a.y, b.x); *d = mk3(b.y, c.x, c.y);
+}
+
+// camera rays of a batch (path_trace.cu:155-165): path i = ss * tile_n + pixel-in-tile, live slot i
+__global__ void __launch_bounds__(kWfBlock) k_wf_generate(DevScene sc, DevRender rp, WfBatch b, float4* __restrict__ state, float* __restrict__ rays,
+                                                          int* __restrict__ n_live, unsigned long long* __restrict__ counters) {
+  const int n = b.tile_n * b.ns;
+  const int cap = b.cap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int pixel, cur_s;
+    float pix_c, pix_r;
+    wf_path_ids(rp, b, i, &pixel, &cur_s, &pix_c, &pix_r);
+    const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, 0u, IPT_STREAM_CAMERA, rp.key0, rp.key1);
+    const float x = fmaf(pix_c + u01(rn.x), rp.two_over_w, -1.0f);
+    const float y = fmaf(pix_r + u01(rn.y), -rp.two_over_h, 1.0f);
+    const f3 dl = mk3(x, y, 1.0f);
+    const f3 rpos = mk3(sc.cam[3], sc.cam[7], sc.cam[11]);
+    const f3 rdir = normalize3(mk3(dot3(sc.cam[0], sc.cam[1], sc.cam[2], dl), dot3(sc.cam[4], sc.cam[5], sc.cam[6], dl), dot3(sc.cam[8], sc.cam[9], sc.cam[10], dl)));
+    state[0 * (size_t)cap + i] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(i));
+    state[1 * (size_t)cap + i] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(WF_EXT_VALID));
+    state[2 * (size_t)cap + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    state[3 * (size_t)cap + i] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    state[4 * (size_t)cap + i] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+    state[5 * (size_t)cap + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    wf_store_ray(rays, (size_t)i, rpos, rdir);
+    wf_store_ray(rays, (size_t)cap + i, rpos, mk3(0.0f, 0.0f, 0.0f));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *n_live = n;
+    if (counters) { atomicAdd(counters + 0, (unsigned long long)n); atomicAdd(counters + 1, (unsigned long long)n); }
+  }
+}
+
+// one bounce of shading for every live path: second half of directLighting of the previous bounce
+// ([D] of k_paths), then radiance() of this bounce's hit ([A] of k_paths); survivors are appended to the
+// next bounce's arrays
+__global__ void __launch_bounds__(kWfBlock, 4) k_wf_shade(DevScene sc, DevRender rp, WfBatch b, int bounce, const float4* __restrict__ sin_, float4* __restrict__ sout,
+                                                       const float* __restrict__ rin, float* __restrict__ rout, const int* __restrict__ hit_tri,
+                                                       const float* __restrict__ hit_t, const int* __restrict__ n_in, int* __restrict__ n_out,
+                                                       float* __restrict__ lsamp, unsigned long long* __restrict__ counters) {
+  const int nT = sc.nT, nE = sc.nE;
+  const size_t cap = (size_t)b.cap;
+  const int n = *n_in;
+  const bool PLAIN = sc.plain != 0;
+  const float4* __restrict__ mat = sc.mat;
+  const float4* __restrict__ slight = sc.light;
+  const f3 zero3 = mk3(0.0f, 0.0f, 0.0f);
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned n_ext = 0, n_shadow = 0;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    const int j = base + (int)threadIdx.x;
+    bool alive = j < n;
+    float m0 = 1.0f, m1 = 1.0f, m2 = 1.0f, q0 = 1.0f, q1 = 1.0f, q2 = 1.0f;
+    float L0 = 0.0f, L1 = 0.0f, L2 = 0.0f, e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+    float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
+    int path = 0;
+    bool ext_valid = false, sh_valid = false, end_after = false;
+    f3 sh_org = zero3, sh_dir = zero3, rpos = zero3, rdir = zero3;
+    int sh_light = -1;
+    float sh_cos = 0.0f, sh_pt = 1.0f;
+    if (alive) {
+      const float4 S0 = sin_[0 * cap + j], S1 = sin_[1 * cap + j], S2 = sin_[2 * cap + j], S3 = sin_[3 * cap + j], S4 = sin_[4 * cap + j], S5 = sin_[5 * cap + j];
+      m0 = S0.x; m1 = S0.y; m2 = S0.z; path = __float_as_int(S0.w);
+      q0 = S1.x; q1 = S1.y; q2 = S1.z;
+      const int fl = __float_as_int(S1.w);
+      L0 = S2.x; L1 = S2.y; L2 = S2.z; sh_cos = S2.w;
+      e0 = S3.x; e1 = S3.y; e2 = S3.z; sh_pt = S3.w;
+      d0 = S4.x; d1 = S4.y; d2 = S4.z; sh_light = __float_as_int(S4.w);
+      f0 = S5.x; f1 = S5.y; f2 = S5.z;
+      const bool was_ext = (fl & WF_EXT_VALID) != 0, was_sh = (fl & WF_SH_VALID) != 0, was_end = (fl & WF_END_AFTER) != 0;
+      // ---- [D] of the previous bounce (path_trace.cu:73-88, 176-180) ----
+      if (was_sh) {
+        d0 = d1 = d2 = 0.0f;
+        const int hs_tri = hit_tri[cap + j];
+        const float hs_t = hit_t[cap + j];
+        f3 so, sd;
+        wf_load_ray(rin, cap + j, &so, &sd);
+        if (hs_tri >= 0) {
+          const float4 lmb = __ldg(&mat[1 * nT + sh_light]);
+          const f3 shit = mk3(fmaf(sd.x, hs_t, so.x), fmaf(sd.y, hs_t, so.y), fmaf(sd.z, hs_t, so.z));
+          const f3 lfn = xyz(__ldg(&mat[3 * nT + sh_light]));
+          const f3 ln = PLAIN ? lfn : shading_normal(sc, sh_light, __float_as_int(lmb.w), lfn, shit);
+          const float cos_tp = -dot3(ln, sd);
+          if (!(cos_tp < 0.0f) && hs_tri == sh_light) {
+            const float g = (sh_cos * cos_tp) / ((hs_t * hs_t) * sh_pt);
+            d0 = f0 * (lmb.x * g); d1 = f1 * (lmb.y * g); d2 = f2 * (lmb.z * g);
+          }
+        }
+        L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2);
+        q0 = m0; q1 = m1; q2 = m2;
+        if (was_end) alive = false;
+      }
+      // ---- [A] this bounce's hit (path_trace.cu:111-144) ----
+      if (alive && was_ext) {
+        const int tri = hit_tri[j];
+        const float ht = hit_t[j];
+        wf_load_ray(rin, (size_t)j, &rpos, &rdir);
+        if (tri < 0) {
+          L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2);
+          alive = false;
+        } else {
+          int pixel, cur_s;
+          float pix_c, pix_r;
+          wf_path_ids(rp, b, path, &pixel, &cur_s, &pix_c, &pix_r);
+          const float4 ma = __ldg(&mat[tri]), mb = __ldg(&mat[1 * nT + tri]);
+          const int flags = __float_as_int(mb.w);
+          const f3 face_n = xyz(__ldg(&mat[3 * nT + tri]));
+          const f3 hit = mk3(fmaf(rdir.x, ht, rpos.x), fmaf(rdir.y, ht, rpos.y), fmaf(rdir.z, ht, rpos.z));
+          const f3 ns = PLAIN ? face_n : shading_normal(sc, tri, flags, face_n, hit);
+          if (bounce == 0) { e0 = mb.x; e1 = mb.y; e2 = mb.z; }
+          const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.key0, rp.key1);
+          if (nE > 0) {
+            const float u_pick = u16(rn.x >> 16), r1 = u16(rn.y >> 16), r2 = u16(rn.y & 0xffffu);
+            int li = 0;
+            while (li < nE - 1 && !(__ldg(&slight[3 * li]).w >= u_pick)) li++;
+            const float4 la = __ldg(&slight[3 * li]), lb = __ldg(&slight[3 * li + 1]), lc = __ldg(&slight[3 * li + 2]);
+            const float sq = sqrtf(r1);
+            const float c1 = 1.0f - sq, c2 = sq * (1.0f - r2), c3 = r2 * sq;
+            const f3 ep = mk3(fmaf(c3, lc.x, fmaf(c2, lb.x, c1 * la.x)), fmaf(c3, lc.y, fmaf(c2, lb.y, c1 * la.y)), fmaf(c3, lc.z, fmaf(c2, lb.z, c1 * la.z)));
+            const f3 toLight = normalize3(ep - hit);
+            const float cos_theta = dot3(ns, toLight);
+            if (!(cos_theta < 0.0f)) {
+              sh_valid = true;
+              sh_org = hit; sh_dir = toLight;
+              sh_light = __float_as_int(lc.w);
+              sh_cos = cos_theta; sh_pt = lb.w;
+              f0 = ma.x; f1 = ma.y; f2 = ma.z;
+              if (!PLAIN && (flags & TRI_ANY_KS)) {
+                const float4 mc = __ldg(&mat[4 * nT + tri]);
+                const float co = phong_coeff(ns, rdir, toLight, ma.w);
+                f0 = fmaf(mc.x, co, f0); f1 = fmaf(mc.y, co, f1); f2 = fmaf(mc.z, co, f2);
+              }
+            }
+          }
+          const bool depth_ok = (rp.max_depth <= 0) || (bounce + 1 < rp.max_depth);
+          if (u16(rn.x & 0xffffu) < rp.p_rr && depth_ok) {
+            f3 nd;
+            float p_sample = IPT_INV_PI_F;
+            if (!PLAIN && (flags & TRI_SPECULAR)) {
+              nd = sample_specular_dir(face_n, ma.w, u01(rn.z), u01(rn.w), &p_sample);
+            } else {
+              float sphi, cphi;
+              sincos2pi(u01(rn.z), &sphi, &cphi);
+              const float ut = u01(rn.w);
+              const float cth = sqrtf(ut), sth = sqrtf(1.0f - ut);
+              const f3 hemi = mk3(sth * cphi, sth * sphi, cth);
+              if (flags & TRI_NEG_Z) {
+                nd = -hemi;
+              } else {
+                const float4 r0 = __ldg(&mat[5 * nT + tri]), r1 = __ldg(&mat[6 * nT + tri]), r2 = __ldg(&mat[7 * nT + tri]);
+                nd = mk3(dot3(r0.x, r0.y, r0.z, hemi), dot3(r1.x, r1.y, r1.z, hemi), dot3(r2.x, r2.y, r2.z, hemi));
+              }
+              nd = normalize3(nd);
+            }
+            const float cosn = dot3(nd, ns);
+            const float4 mp = __ldg(&mat[2 * nT + tri]);
+            float i0 = mp.x, i1 = mp.y, i2 = mp.z;
+            float coeff = cosn * rp.c_diff;
+            if (!PLAIN && (flags & TRI_ANY_KS)) {
+              const float4 mc = __ldg(&mat[4 * nT + tri]);
+              const float co = phong_coeff(ns, rdir, nd, ma.w);
+              i0 = fmaf(mc.x, co, i0); i1 = fmaf(mc.y, co, i1); i2 = fmaf(mc.z, co, i2);
+              if (flags & TRI_SPECULAR) coeff = (cosn / p_sample) / rp.p_rr;
+            }
+            m0 = (m0 * i0) * coeff; m1 = (m1 * i1) * coeff; m2 = (m2 * i2) * coeff;
+            rpos = hit;
+            rdir = nd;
+            ext_valid = true;
+          } else {
+            end_after = true;
+          }
+          if (!sh_valid) {
+            d0 = d1 = d2 = 0.0f;
+            L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2);
+            q0 = m0; q1 = m1; q2 = m2;
+            if (end_after) alive = false;
+          }
+        }
+      }
+      if (!alive) {   // path finished: its radiance goes to the per-sample buffer (summed in sample order by k_wf_accumulate)
+        lsamp[0 * cap + path] = L0; lsamp[1 * cap + path] = L1; lsamp[2 * cap + path] = L2;
+      }
+    }
+    // ---- append survivors (one atomic per warp) ----
+    const unsigned amask = __ballot_sync(kFull, alive);
+    if (amask) {
+      const int leader = __ffs(amask) - 1;
+      int basej = 0;
+      if ((int)lane == leader) basej = atomicAdd(n_out, __popc(amask));
+      basej = __shfl_sync(kFull, basej, leader);
+      if (alive) {
+        const size_t jn = (size_t)basej + __popc(amask & ((1u << lane) - 1u));
+        const int fl = (ext_valid ? WF_EXT_VALID : 0) | (sh_valid ? WF_SH_VALID : 0) | (end_after ? WF_END_AFTER : 0);
+        sout[0 * cap + jn] = make_float4(m0, m1, m2, __int_as_float(path));
+        sout[1 * cap + jn] = make_float4(q0, q1, q2, __int_as_float(fl));
+        sout[2 * cap + jn] = make_float4(L0, L1, L2, sh_cos);
+        sout[3 * cap + jn] = make_float4(e0, e1, e2, sh_pt);
+        sout[4 * cap + jn] = make_float4(d0, d1, d2, __int_as_float(sh_light));
+        sout[5 * cap + jn] = make_float4(f0, f1, f2, 0.0f);
+        wf_store_ray(rout, jn, rpos, ext_valid ? rdir : zero3);
+        wf_store_ray(rout, cap + jn, sh_org, sh_valid ? sh_dir : zero3);
+        n_ext += ext_valid ? 1u : 0u;
+        n_shadow += sh_valid ? 1u : 0u;
+      }
+    }
+  }
+  if (counters) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_ext += __shfl_down_sync(kFull, n_ext, o);
+      n_shadow += __shfl_down_sync(kFull, n_shadow, o);
+    }
+    if (lane == 0 && (n_ext | n_shadow)) {
+      atomicAdd(counters + 1, (unsigned long long)n_ext);
+      atomicAdd(counters + 2, (unsigned long long)n_shadow);
+    }
+  }
+}
+
+// toneMap's running sum (path_trace.cu:190-193) over the batch: samples in order, continuing the group's partial sum
+__global__ void __launch_bounds__(kWfBlock) k_wf_accumulate(const float* __restrict__ lsamp, WfBatch b, int group, int groups, int first, float inv_spp,
+                                                            float* __restrict__ partial) {
+  const int pl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pl >= b.tile_n) return;
+  float* dst = partial + ((size_t)(b.tile_p0 + pl) * groups + group) * 3;
+  float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+  if (!first) { p0 = dst[0]; p1 = dst[1]; p2 = dst[2]; }
+  const size_t cap = (size_t)b.cap;
+  for (int ss = 0; ss < b.ns; ss++) {
+    const size_t path = (size_t)ss * b.tile_n + pl;
+    p0 += lsamp[0 * cap + path] * inv_spp; p1 += lsamp[1 * cap + path] * inv_spp; p2 += lsamp[2 * cap + path] * inv_spp;
+  }
+  dst[0] = p0; dst[1] = p1; dst[2] = p2;
+}
+
+// ---- wavefront forward pass ------------------------------------------------------------------------------
+// workspace layout (bytes, all 256-aligned): state A, state B (6 float4 x cap each), rays A, rays B
+// (2 x 6 floats x cap each), hit ids, hit t (2 x cap each), per-sample radiance (3 x cap), control words
+static size_t wf_align(size_t b) { return (b + 255) & ~(size_t)255; }
+size_t wavefront_workspace_bytes(int cap) {
+  const size_t c = (size_t)cap;
+  return 2 * wf_align(6 * c * sizeof(float4)) + 2 * wf_align(12 * c * sizeof(float)) + wf_align(2 * c * sizeof(int)) + wf_align(2 * c * sizeof(float)) +
+         wf_align(3 * c * sizeof(float)) + 256;
+}
+
+cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* workspace, int cap, float* partial, unsigned long long* counters,
+                             int sm_count, int* host_live, unsigned long long* n_launches, cudaStream_t st) {
+  const size_t c = (size_t)cap;
+  char* w = (char*)workspace;
+  float4* state[2];
+  float* rays[2];
+  state[0] = (float4*)w; w += wf_align(6 * c * sizeof(float4));
+  state[1] = (float4*)w; w += wf_align(6 * c * sizeof(float4));
+  rays[0] = (float*)w; w += wf_align(12 * c * sizeof(float));
+  rays[1] = (float*)w; w += wf_align(12 * c * sizeof(float));
+  int* hit_tri = (int*)w; w += wf_align(2 * c * sizeof(int));
+  float* hit_t = (float*)w; w += wf_align(2 * c * sizeof(float));
+  float* lsamp = (float*)w; w += wf_align(3 * c * sizeof(float));
+  unsigned long long* trace_counter = (unsigned long long*)w;   // [0]
+  int* n_live = (int*)(w + 16);                                 // [0], [1]: ping-pong live counts
+
+  const int shade_grid = sm_count * 8;
+  cudaError_t e = cudaSuccess;
+
+  const int tile_cap = std::min(rp.n_pix, cap);
+  const bool unbounded = rp.max_depth <= 0;
+  for (int p0 = 0; p0 < rp.n_pix; p0 += tile_cap) {
+    const int tn = std::min(tile_cap, rp.n_pix - p0);
+    const int nsb = std::max(1, std::min(rp.group_samples, cap / tn));
+    for (int g = 0; g < rp.groups; g++) {
+      const int g_begin = g * rp.group_samples, g_end = std::min(rp.spp, g_begin + rp.group_samples);
+      for (int s0 = g_begin; s0 < g_end; s0 += nsb) {
+        WfBatch b;
+        b.cap = cap; b.tile_p0 = p0; b.tile_n = tn; b.s0 = s0; b.ns = std::min(nsb, g_end - s0);
+        const int n_paths = b.tile_n * b.ns;
+        int cur = 0;
+        k_wf_generate<<<std::min((n_paths + kWfBlock - 1) / kWfBlock, shade_grid), kWfBlock, 0, st>>>(sc, rp, b, state[0], rays[0], n_live + 0, counters);
+        *n_launches += 1;
+        for (int bounce = 0;; bounce++) {
+          if (!unbounded && bounce > rp.max_depth) break;
+          e = cudaMemsetAsync(n_live + (cur ^ 1), 0, sizeof(int), st);
+          if (e != cudaSuccess) return e;
+          e = launch_trace_bounce(sc, rays[cur], n_live + cur, cap, hit_tri, hit_t, trace_counter, sm_count, n_launches, st);
+          if (e != cudaSuccess) return e;
+          k_wf_shade<<<shade_grid, kWfBlock, 0, st>>>(sc, rp, b, bounce, state[cur], state[cur ^ 1], rays[cur], rays[cur ^ 1], hit_tri, hit_t, n_live + cur,
+                                                     n_live + (cur ^ 1), lsamp, counters);
+          *n_launches += 1;
+          cur ^= 1;
+          if (unbounded) {
+            e = cudaMemcpyAsync(host_live, n_live + cur, sizeof(int), cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return e;
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            if (*host_live == 0) break;
+          }
+        }
+        k_wf_accumulate<<<(b.tile_n + kWfBlock - 1) / kWfBlock, kWfBlock, 0, st>>>(lsamp, b, g, rp.groups, s0 == g_begin ? 1 : 0, rp.inv_spp, partial);
+        *n_launches += 1;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+      }
+    }
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace ipt
