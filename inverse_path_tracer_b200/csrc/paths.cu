@@ -60,13 +60,17 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   // brute-force set: the whole scene, or in BVH mode the large triangles kept out of the tree
   if (!BVH || sc.nGroups > 0) ss = stage_small_scene(sc, cursor, &cursor);
   float4* smat = cursor;
-  float4* slight = smat + (BVH ? 0 : kMatStride * nT);
-  float* sacc = reinterpret_cast<float*>(slight + 3 * nE);
+  float4* slight_s = smat + (BVH ? 0 : kMatStride * nT);
+  const bool lights_staged = !BVH || nE <= kLightSmemMax;   // an emissive mesh stays in global memory (BVH scenes only)
+  float* sacc = reinterpret_cast<float*>(slight_s + (lights_staged ? 3 * nE : 0));
+  const float4* __restrict__ slight = lights_staged ? slight_s : sc.light;
   const float4* __restrict__ mat = BVH ? sc.mat : smat;
   if (!BVH) {
     for (int i = threadIdx.x; i < kMatStride * nT; i += blockDim.x) smat[i] = sc.mat[i];
   }
-  for (int i = threadIdx.x; i < 3 * nE; i += blockDim.x) slight[i] = sc.light[i];
+  if (lights_staged) {
+    for (int i = threadIdx.x; i < 3 * nE; i += blockDim.x) slight_s[i] = sc.light[i];
+  }
   if (MODE != MODE_RENDER && out.acc_in_smem == 1) {
     for (int i = threadIdx.x; i < out.acc_stride; i += blockDim.x) sacc[i] = 0.0f;
   }
@@ -237,8 +241,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         //      point; the shadow ray itself goes into this trip's dual intersection
         if (nE > 0) {
           const float u_pick = u16(rn.x >> 16), r1 = u16(rn.y >> 16), r2 = u16(rn.y & 0xffffu);
-          int li = 0;
-          while (li < nE - 1 && !(slight[3 * li].w >= u_pick)) li++;
+          const int li = pick_light(slight, nE, u_pick);
           const float4 la = slight[3 * li], lb = slight[3 * li + 1], lc = slight[3 * li + 2];
           const float sq = sqrtf(r1);
           const float c1 = 1.0f - sq, c2 = sq * (1.0f - r2), c3 = r2 * sq;
@@ -575,7 +578,8 @@ __global__ void k_set_kd(float4* __restrict__ mat, const float* __restrict__ kd,
 // ------------------------------------------------------------------------------------------------
 
 size_t paths_smem_bytes(const DevScene& sc, int acc_floats) {
-  size_t b = (size_t)3 * sc.nE * sizeof(float4) + (size_t)acc_floats * sizeof(float);
+  size_t b = (size_t)acc_floats * sizeof(float);
+  if (!sc.use_bvh || sc.nE <= kLightSmemMax) b += (size_t)3 * sc.nE * sizeof(float4);
   if (!sc.use_bvh) b += small_scene_smem_bytes(sc.nSlots, sc.nGroups) + (size_t)kMatStride * sc.nT * sizeof(float4);
   else b += bvh_stack_bytes(sc) + (sc.nGroups > 0 ? small_scene_smem_bytes(sc.nSlots, sc.nGroups) : 0);
   return b;

@@ -46,4 +46,24 @@ static __device__ __noinline__ f3 sample_specular_dir(f3 N, float shininess, flo
   return normalize3(nd);
 }
 
+// directLighting's area-proportional pick (path_trace.cu:39-51): the first emissive triangle whose cumulative
+// probability reaches u, the last one if none does.  Same index as the reference's linear scan; emissive meshes
+// (thousands of lights) are searched by bisection because the cdf is non-decreasing.
+__device__ __forceinline__ int pick_light(const float4* __restrict__ lights, int nE, float u) {
+  if (nE <= 16) {
+    int li = 0;
+    while (li < nE - 1 && !(lights[3 * li].w >= u)) li++;
+    return li;
+  }
+  int lo = 0, hi = nE - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (lights[3 * mid].w >= u) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// lights are staged into shared memory by k_paths when they fit this budget (512 emissive triangles)
+constexpr int kLightSmemMax = 512;
+
 }  // namespace ipt

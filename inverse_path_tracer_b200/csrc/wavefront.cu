@@ -167,8 +167,7 @@ __global__ void __launch_bounds__(kWfBlock, 4) k_wf_shade(DevScene sc, DevRender
           const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.key0, rp.key1);
           if (nE > 0) {
             const float u_pick = u16(rn.x >> 16), r1 = u16(rn.y >> 16), r2 = u16(rn.y & 0xffffu);
-            int li = 0;
-            while (li < nE - 1 && !(__ldg(&slight[3 * li]).w >= u_pick)) li++;
+            const int li = pick_light(slight, nE, u_pick);
             const float4 la = __ldg(&slight[3 * li]), lb = __ldg(&slight[3 * li + 1]), lc = __ldg(&slight[3 * li + 2]);
             const float sq = sqrtf(r1);
             const float c1 = 1.0f - sq, c2 = sq * (1.0f - r2), c3 = r2 * sq;

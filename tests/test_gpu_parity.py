@@ -169,6 +169,35 @@ def test_large_triangle_set_does_not_change_results(ipt, oracle):
     assert sizes == [18, 7, 0]
 
 
+def test_emissive_mesh_many_lights(ipt, oracle, tmp_path):
+    """an emissive mesh: 1280 + 2 lights.  The light pick becomes a bisection over the cdf (same index as the reference's
+    linear scan) and the light table no longer fits the megakernel's shared-memory budget (global-memory path)."""
+    src = open(os.path.join(ASSETS, "shapes", "sphere.obj")).read()
+    obj, mtl = tmp_path / "glow.obj", tmp_path / "glow.mtl"
+    obj.write_text("mtllib glow.mtl\nusemtl glow\n" + src)
+    mtl.write_text("newmtl glow\nKd 0.6 0.5 0.4\nKe 1.5 1.2 0.9\n")
+    objects = scene_objects("cornell") + [{"pos": [0.3, -1.0, 4.0], "ori": [0, 0.3, 0], "scl": [1.2, 1.2, 1.2], "obj": str(obj), "mtl": str(mtl)}]
+    g, o = _pair(ipt, oracle, objects)
+    assert g.uses_bvh and g.nE == o.nE == 1282
+    po = oracle.make_params(40, 32, 6, max_depth=5, seed=21)
+    img_o, cnt_o = o.render(po)
+    try:
+        for integ in (1, 2):
+            ipt.set_integrator(integ, 0)
+            img_g, cnt_g = g.render(ipt.default_params(width=40, height=32, spp=6, max_depth=5, seed=21))
+            assert cnt_g == cnt_o, integ
+            assert img_g.tobytes() == img_o.tobytes(), "integrator %d: max abs diff %g" % (integ, np.abs(img_g - img_o).max())
+    finally:
+        ipt.set_integrator(0, 0)
+    # the adjoint (megakernel, lights in global memory) against the oracle's
+    target = np.random.RandomState(2).randint(0, 256, (32, 40, 3)).astype(np.uint8)
+    loss_g, grad_g, _ = g.render_grad(ipt.default_params(width=40, height=32, spp=6, max_depth=5, seed=21), target)
+    loss_o, grad_o = o.render_grad(po, target)[:2]
+    assert abs(loss_g - loss_o) <= 1e-6 * abs(loss_o)
+    scale = np.abs(grad_o).max()
+    assert np.abs(grad_g - grad_o).max() <= 1e-3 * scale
+
+
 def test_row_sharding_and_determinism(ipt, oracle):
     g = ipt.Scene(_scene0(oracle), asset_root=ASSETS)
     p = ipt.default_params(width=96, height=80, spp=32, seed=3)
