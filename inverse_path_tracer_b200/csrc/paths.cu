@@ -45,9 +45,13 @@ __device__ __forceinline__ int adj_light(const AdjVertex& v) { return __float_as
 // PLAIN is a compile-time promise that no triangle has per-vertex normals or a specular lobe (true for every
 // asset the reference ships); the Phong / vertex-normal code is then not compiled into the kernel at all.
 #ifndef IPT_SWEEP_PER_TRIP
-#define IPT_SWEEP_PER_TRIP 2
+#define IPT_SWEEP_PER_TRIP 4
 #endif
-constexpr int kSweepPerTrip = IPT_SWEEP_PER_TRIP;   // adjoint sweep vertices advanced per trip of the main loop
+constexpr int kSweepPerTrip = IPT_SWEEP_PER_TRIP;   // adjoint sweep: at most this many vertices per lane per trip of the main loop ...
+#ifndef IPT_SWEEP_QUORUM
+#define IPT_SWEEP_QUORUM 4
+#endif
+constexpr int kSweepQuorum = IPT_SWEEP_QUORUM;      // ... while at least this many lanes of the warp have one pending
 template <int MODE, bool BVH, bool PLAIN>
 __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRender rp, DevOut out) {
   extern __shared__ float4 smem[];
@@ -457,8 +461,12 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       }
     }
     if (MODE == MODE_GRAD) {
+      // reconverge first: the lanes arrive from different arms of [D] and the point of the deferred sweep is that they
+      // run it together
 #pragma unroll 1
       for (int r = 0; r < kSweepPerTrip; r++) {
+        const unsigned pending = __ballot_sync(kFull, sw_k >= 0);
+        if (__popc(pending) < kSweepQuorum) break;
         if (sw_k >= 0) sweep_step();
       }
     }
