@@ -29,6 +29,10 @@ constexpr int kInnerQuorum = IPT_INNER_QUORUM;
 #define IPT_FETCH_QUORUM 8
 #endif
 constexpr int kFetchQuorum = IPT_FETCH_QUORUM;
+#ifndef IPT_RAY_CHUNK
+#define IPT_RAY_CHUNK 128
+#endif
+constexpr int kRayChunk = IPT_RAY_CHUNK;
 
 template <bool STATS>
 __global__ void __launch_bounds__(kBlock) k_trace_rays_bvh(DevScene sc, const float* __restrict__ rays, int n_direct, const int* __restrict__ n_live, int cap,
@@ -49,6 +53,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays_bvh(DevScene sc, const fl
   r.best_t = INFINITY; r.best_i = -1; r.sp = 0;
   long long idx = -1;
   bool exhausted = false;       // the batch has no ray left for this lane
+  int chunk_next = 0, chunk_end = 0;   // the warp's current chunk of ray indices (warp-uniform; a batch has < 2^31 rays)
   for (;;) {
     // ---- fetch ----
     const bool want = r.cur == kBvhDone && !exhausted;
@@ -57,12 +62,26 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays_bvh(DevScene sc, const fl
     // the others have nothing to do either
     if (wm && (__popc(wm) >= kFetchQuorum || __ballot_sync(kFull, r.cur != kBvhDone) == 0u)) {
       if (want && idx >= 0) { tri[idx] = r.best_i; tout[idx] = r.best_t; idx = -1; }
-      const int leader = __ffs(wm) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(wm));
-      base = __shfl_sync(kFull, base, leader);
+      // rays are claimed from the global counter kRayChunk at a time per warp (one atomic per chunk, not per refill:
+      // every warp of the grid hits the same address); a refill takes what is left of the warp's chunk first
+      const int need = __popc(wm), rank = __popc(wm & ((1u << lane) - 1u));
+      const int left = chunk_end - chunk_next;
+      long long mine;
+      if (need > left) {
+        const int leader = __ffs(wm) - 1;
+        unsigned long long fresh = 0;
+        if ((int)lane == leader) fresh = atomicAdd(counter, (unsigned long long)kRayChunk);
+        fresh = __shfl_sync(kFull, fresh, leader);
+        // a claim far beyond the batch (the counter keeps growing while warps drain) is clamped: it is exhausted anyway
+        const int fb = (int)min(fresh, (unsigned long long)0x7fff0000u);
+        mine = rank < left ? (long long)(chunk_next + rank) : (long long)fb + (rank - left);
+        chunk_next = fb + (need - left);
+        chunk_end = fb + kRayChunk;
+      } else {
+        mine = chunk_next + rank;
+        chunk_next += need;
+      }
       if (want) {
-        const long long mine = (long long)base + __popc(wm & ((1u << lane) - 1u));
         if (mine >= total) {
           exhausted = true;
         } else {
