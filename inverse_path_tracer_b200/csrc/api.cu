@@ -423,6 +423,11 @@ static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan)
   rp.row_begin = rb;
   rp.row_step = step;
   rp.n_pix = rows * p->width;
+  // work-item index -> (pixel, group) and pixel -> (row, column) by multiplication (an integer division per item is a
+  // visible cost when items are small)
+  auto magic = [](unsigned d) { return d > 1 ? ~0ull / d + 1 : 0ull; };   // ceil(2^64 / d) for d that is not a power of two; exact use below
+  rp.magic_groups = magic((unsigned)rp.groups);
+  rp.magic_width = magic((unsigned)p->width);
   plan->rows = rows;
   return 0;
 }

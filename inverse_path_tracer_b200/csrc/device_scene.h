@@ -60,6 +60,7 @@ struct DevRender {
   int row_begin;        // first image row of this shard
   int row_step;         // the shard owns rows row_begin, row_begin + row_step, ... (interleaved sharding)
   int n_pix;            // pixels in this shard (compact local index = local_row * width + column)
+  unsigned long long magic_groups, magic_width;   // ceil(2^64 / d): floor(x / d) = __umul64hi(x, magic) for x < 2^32, d > 1
 };
 
 // counters[0..2] = paths, extension rays, shadow rays

@@ -349,10 +349,12 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
           if (my < n_items) {
             have_item = true;
             item = my;
-            const int pix_local = (int)(my / rp.groups);
+            // floor(my / groups) and floor(pixel / width) by multiplication with ceil(2^64 / d) (exact below 2^32)
+            const int pix_local = rp.groups == 1 ? (int)my
+                                  : (my < 0x100000000ll ? (int)__umul64hi((unsigned long long)my, rp.magic_groups) : (int)(my / rp.groups));
             const int g = (int)(my - (long long)pix_local * rp.groups);
             {
-              const int lr = pix_local / rp.width;                 // one integer division per work item
+              const int lr = rp.width == 1 ? pix_local : (int)__umul64hi((unsigned long long)pix_local, rp.magic_width);
               const int c = pix_local - lr * rp.width;
               const int r = rp.row_begin + lr * rp.row_step;       // interleaved row shards
               pixel = r * rp.width + c;                            // global pixel index: RNG counter, target lookup
