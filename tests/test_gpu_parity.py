@@ -460,3 +460,13 @@ def test_edge_case_scenes(ipt, oracle, tmp_path):
     a_, ca_ = g.render(ipt.default_params(width=8, height=8, spp=2, p_rr=1.0, max_depth=4, seed=2))
     b_, cb_ = o.render(oracle.make_params(8, 8, 2, p_rr=1.0, max_depth=4, seed=2))
     assert ca_ == cb_ and a_.tobytes() == b_.tobytes() and 3 * ca_["paths"] < ca_["ext_rays"] <= 4 * ca_["paths"]   # a few paths leave through the open front
+
+
+def test_default_group_rule_matches_oracle(ipt, oracle):
+    """both sides resolve group_samples = -1 with the same size rule, and 0 means one running sum per pixel"""
+    g, o = _pair(ipt, oracle, scene_objects("cornell"))
+    for gs in (-1, 0, 5):
+        pg = ipt.default_params(width=40, height=24, spp=12, max_depth=4, seed=8, group_samples=gs)
+        po = oracle.make_params(40, 24, 12, max_depth=4, seed=8, group_samples=gs)
+        assert g.render(pg)[0].tobytes() == o.render(po)[0].tobytes(), gs
+    assert ipt.default_params().group_samples == -1
