@@ -30,7 +30,7 @@ __device__ __forceinline__ f3 shading_normal(const DevScene& sc, int tri, int fl
 static __device__ __noinline__ float phong_coeff(f3 nrm, f3 w, f3 w_i, float n) {
   const float k = 2.0f * dot3(nrm, w_i);
   const f3 refl = mk3(fmaf(k, nrm.x, -w_i.x), fmaf(k, nrm.y, -w_i.y), fmaf(k, nrm.z, -w_i.z));
-  const float pw = powf(dot3(refl, w), n);
+  const float pw = canon_pow(dot3(refl, w), n);
   return ((n + 2.0f) / 2.0f / IPT_PI_F) * fmaxf(pw, 0.0f);
 }
 
@@ -38,11 +38,11 @@ static __device__ __noinline__ float phong_coeff(f3 nrm, f3 w, f3 w_i, float n) 
 static __device__ __noinline__ f3 sample_specular_dir(f3 N, float shininess, float u_phi, float u_theta, float* p_sample) {
   float sphi, cphi;
   sincos2pi(u_phi, &sphi, &cphi);
-  const float cth = powf(u_theta, 1.0f / (shininess + 1.0f));
+  const float cth = canon_pow(u_theta, 1.0f / (shininess + 1.0f));
   const float sth = sqrtf(fmaxf(0.0f, 1.0f - cth * cth));
   const f3 hemi = mk3(sth * cphi, sth * sphi, cth);
   const f3 nd = (N.z == -1.0f) ? -hemi : rotate_from_z(N, hemi);
-  *p_sample = powf((shininess + 1.0f) * cth, shininess);
+  *p_sample = canon_pow((shininess + 1.0f) * cth, shininess);
   return normalize3(nd);
 }
 

@@ -893,13 +893,65 @@ static void frame_from_z(V3 N, float R[3][3]) {
   R[2][0] = -twy;       R[2][1] = twx;        R[2][2] = 1.0f - (txx + tyy);
 }
 
+// pow() of the specular lobe, canon v4: (float) 2^(y log2|x|) in double with a fixed
+// operation order -- fdlibm's log kernel on the mantissa folded into (sqrt(1/2), sqrt(2)], a degree-13 Taylor
+// series for e^r -- because glibc's powf and CUDA's powf differ by ulps.  Special cases as pow().
+static double pow_log2(double x) {
+  uint64_t u;
+  memcpy(&u, &x, sizeof u);
+  int ex = (int)((u >> 52) & 0x7ffu) - 1023;
+  u = (u & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+  double m;
+  memcpy(&m, &u, sizeof m);
+  if (m > 1.4142135623730951) { m *= 0.5; ex += 1; }
+  const double f = m - 1.0, s = f / (2.0 + f), z = s * s;
+  static const double Lg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,
+                               1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01};
+  double R = Lg[6];
+  for (int i = 5; i >= 0; i--) R = std::fma(R, z, Lg[i]);
+  R = R * z;
+  const double hfsq = 0.5 * f * f;
+  const double ln1p = f - (hfsq - s * (hfsq + R));
+  return std::fma(ln1p, 1.4426950408889634074, (double)ex);
+}
+static double pow_exp2(double t) {
+  if (t > 1024.0) return (double)INFINITY;
+  if (t < -1100.0) return 0.0;
+  const double k = std::floor(t + 0.5);
+  const double r = (t - k) * 0.69314718055994530942;
+  static const double inv_fact[14] = {1.0, 1.0, 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0, 1.0 / 362880.0,
+                                      1.0 / 3628800.0, 1.0 / 39916800.0, 1.0 / 479001600.0, 1.0 / 6227020800.0};
+  double p = inv_fact[13];
+  for (int i = 12; i >= 0; i--) p = std::fma(p, r, inv_fact[i]);
+  const int ki = (int)k, k1 = ki / 2, k2 = ki - k1;
+  const uint64_t b1 = (uint64_t)(k1 + 1023) << 52, b2 = (uint64_t)(k2 + 1023) << 52;
+  double s1, s2;
+  memcpy(&s1, &b1, sizeof s1);
+  memcpy(&s2, &b2, sizeof s2);
+  return (p * s1) * s2;
+}
+static float canon_pow(float x, float y) {
+  if (y == 0.0f) return 1.0f;
+  if (x != x || y != y) return x + y;
+  const float ax = std::fabs(x);
+  const bool y_int = std::floor(y) == y;
+  const bool y_odd = y_int && std::fabs(y) < 16777216.0f && (((long long)y) & 1ll) != 0;
+  if (x < 0.0f && !y_int) return NAN;
+  float r;
+  if (ax == 0.0f) r = y > 0.0f ? 0.0f : INFINITY;
+  else if (ax == INFINITY) r = y > 0.0f ? INFINITY : 0.0f;
+  else if (y == INFINITY || y == -INFINITY) r = (ax == 1.0f) ? 1.0f : (((ax > 1.0f) == (y > 0.0f)) ? INFINITY : 0.0f);
+  else r = (float)pow_exp2((double)y * pow_log2((double)ax));
+  return (x < 0.0f && y_odd) ? -r : r;
+}
+
 // sampleNextDir, path_trace.cu:91-109 (identical in inv_path_trace.cu:89-107)
 static float sample_next_dir(V3 normDir, bool isSpecular, float shininess, float u_phi, float u_theta, V3* nextDir) {
   float sphi, cphi;
   sincos2pi(u_phi, &sphi, &cphi);
   float cth, sth;
   if (isSpecular) {
-    cth = powf(u_theta, 1.0f / (shininess + 1.0f));
+    cth = canon_pow(u_theta, 1.0f / (shininess + 1.0f));
     sth = sqrtf(fmaxf(0.0f, 1.0f - cth * cth));
   } else {
     cth = sqrtf(u_theta);            // cos(acos(sqrt(u)))
@@ -915,7 +967,7 @@ static float sample_next_dir(V3 normDir, bool isSpecular, float shininess, float
     nd = mk(dot(mk(R[0][0], R[0][1], R[0][2]), hemi), dot(mk(R[1][0], R[1][1], R[1][2]), hemi), dot(mk(R[2][0], R[2][1], R[2][2]), hemi));
   }
   *nextDir = normalize(nd);
-  return isSpecular ? powf((shininess + 1.0f) * cth, shininess) : kInvPi;
+  return isSpecular ? canon_pow((shininess + 1.0f) * cth, shininess) : kInvPi;
 }
 
 static inline bool has_specular(const Material& m) { return (m.ks[0] != 0.0f || m.ks[1] != 0.0f || m.ks[2] != 0.0f); }
@@ -929,7 +981,7 @@ static void bsdf(const Triangle& tri, V3 hit, V3 w, V3 w_i, bool isDirect, float
     V3 nrm = shading_normal(tri, hit);
     float k = 2.0f * dot(nrm, w_i);
     V3 refl = mk(fmaf(k, nrm.x, -w_i.x), fmaf(k, nrm.y, -w_i.y), fmaf(k, nrm.z, -w_i.z));
-    float pw = powf(dot(refl, w), n);
+    float pw = canon_pow(dot(refl, w), n);
     float coeff = ((n + 2.0f) / 2.0f / kPi) * fmaxf(pw, 0.0f);
     for (int i = 0; i < 3; i++) out[i] = fmaf(tri.mat.ks[i], coeff, out[i]);
   }
@@ -1215,6 +1267,8 @@ static void graph_compress(const std::vector<Edge>& edges, int nT, float* data) 
 using namespace orc;
 
 extern "C" {
+float orc_canon_pow(float x, float y) { return orc::canon_pow(x, y); }
+
 
 struct OrcParams {
   int width, height, spp, max_depth;

@@ -470,3 +470,40 @@ def test_default_group_rule_matches_oracle(ipt, oracle):
         po = oracle.make_params(40, 24, 12, max_depth=4, seed=8, group_samples=gs)
         assert g.render(pg)[0].tobytes() == o.render(po)[0].tobytes(), gs
     assert ipt.default_params().group_samples == -1
+
+
+def _fuzz_scene_cases():
+    path = os.path.join(GOLDEN, "loader_fuzz.npz")
+    return [str(c) for c in np.load(path)["cases"]] if os.path.exists(path) else []
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_fuzz_scenes_bit_exact_all_integrators(ipt, oracle, chunk):
+    """The 48 loader-fuzz meshes (random triangle soups: slivers, crossing faces, random Kd/Ks/Ke/Ns materials, vertex
+    normals, concave polygons) inside the Cornell box: hits, ray counts and images of the brute-force kernel, the BVH
+    megakernel and the wavefront integrator must equal the oracle bit for bit -- including the Phong lobe and specular
+    sampling, whose pow() is part of the canon (canon v4)."""
+    cases = _fuzz_scene_cases()[chunk::4]
+    assert cases
+    cornell = scene_objects("cornell")
+    rng = np.random.RandomState(7 + chunk)
+    rays = np.concatenate([rng.uniform(-2, 2, (3000, 3)) + [0, 0, 4], rng.normal(size=(3000, 3))], 1).astype(np.float32)
+    rays[:, 3:] /= np.linalg.norm(rays[:, 3:], axis=1, keepdims=True)
+    try:
+        for case in cases:
+            objs = [{"pos": [0, 0, 5], "ori": [0.1, 0.2, 0.3], "scl": [1, 1, 1], "obj": "./fuzz/%s.obj" % case, "mtl": "./fuzz/%s.mtl" % case}] + cornell
+            o = oracle.OracleScene(objs, ASSETS)
+            img_o, cnt_o = o.render(oracle.make_params(32, 24, 4, max_depth=5, seed=3))
+            tri_o, t_o = o.trace(rays)
+            for mode in (0, 2):
+                g = ipt.Scene(objs, asset_root=ASSETS, traversal_mode=mode)
+                tri_g, t_g = g.trace(rays)
+                assert np.array_equal(tri_g, tri_o) and t_g.tobytes() == t_o.tobytes(), (case, mode)
+                for integ in ((1,) if mode == 0 else (1, 2)):
+                    ipt.set_integrator(integ, 0)
+                    img_g, cnt_g = g.render(ipt.default_params(width=32, height=24, spp=4, max_depth=5, seed=3))
+                    assert cnt_g == cnt_o, (case, mode, integ)
+                    assert img_g.tobytes() == img_o.tobytes(), (case, mode, integ, float(np.nanmax(np.abs(img_g - img_o))))
+                g.close()
+    finally:
+        ipt.set_integrator(0, 0)
