@@ -407,6 +407,7 @@ static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan)
   DevRender& rp = plan->rp;
   rp.width = p->width; rp.height = p->height; rp.spp = p->spp; rp.max_depth = p->max_depth;
   rp.p_rr = p->p_rr; rp.key0 = p->seed_lo; rp.key1 = p->seed_hi;
+  rp.keys = philox_key_schedule(rp.key0, rp.key1);
   rp.inv_spp = 1.0f / (float)p->spp;
   rp.two_over_w = 2.0f / (float)p->width;
   rp.two_over_h = 2.0f / (float)p->height;

@@ -17,6 +17,8 @@
 //   bvh wide  [4*nNodes] : {L.lo, desc L} {L.hi, desc R} {R.lo, -} {R.hi, -}             64 B / inner node (traversal)
 #pragma once
 #include <cuda_runtime.h>
+
+#include "ipt_math.cuh"
 #include <stdint.h>
 
 namespace ipt {
@@ -55,6 +57,7 @@ struct DevRender {
   float inv_spp;        // 1 / spp (canon v3: toneMap's src[i]/SPP as a product)
   float two_over_w, two_over_h;   // camera raster scale (canon v3)
   uint32_t key0, key1;
+  PhiloxKeys keys;      // round keys of (key0, key1)
   int group_samples;    // samples per work item
   int groups;           // work items per pixel
   int row_begin;        // first image row of this shard

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         const f3 hit = mk3(fmaf(rdir.x, h.t, rpos.x), fmaf(rdir.y, h.t, rpos.y), fmaf(rdir.z, h.t, rpos.z));
         const f3 ns = PLAIN ? face_n : shading_normal(sc, tri, flags, face_n, hit);
         if (MODE != MODE_GRAPH && bounce == 0) { e0 = mb.x; e1 = mb.y; e2 = mb.z; }
-        const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.key0, rp.key1);
+        const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.keys);
         AdjVertex vx;
         if (MODE == MODE_GRAD) { vx.a = make_float4(__int_as_float(tri), 0.0f, __int_as_float(-1), 0.0f); vx.p = make_float4(q0, q1, q2, 0.0f); }
 
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     if (!ext_valid && have_item && s_next < s_end) {
       // camera ray (path_trace.cu:155-165, Ray::transform scene_basics.h:307-319)
       cur_s = s_next++;
-      const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, 0u, IPT_STREAM_CAMERA, rp.key0, rp.key1);
+      const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, 0u, IPT_STREAM_CAMERA, rp.keys);
       const float x = fmaf(pix_c + u01(rn.x), rp.two_over_w, -1.0f);
       const float y = fmaf(pix_r + u01(rn.y), -rp.two_over_h, 1.0f);
       const f3 dl = mk3(x, y, 1.0f);

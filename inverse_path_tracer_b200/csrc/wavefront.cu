@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(DevScene sc, DevRender
     int pixel, cur_s;
     float pix_c, pix_r;
     wf_path_ids(rp, b, i, &pixel, &cur_s, &pix_c, &pix_r);
-    const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, 0u, IPT_STREAM_CAMERA, rp.key0, rp.key1);
+    const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, 0u, IPT_STREAM_CAMERA, rp.keys);
     const float x = fmaf(pix_c + u01(rn.x), rp.two_over_w, -1.0f);
     const float y = fmaf(pix_r + u01(rn.y), -rp.two_over_h, 1.0f);
     const f3 dl = mk3(x, y, 1.0f);
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kWfBlock, 4) k_wf_shade(DevScene sc, DevRender
           const f3 hit = mk3(fmaf(rdir.x, ht, rpos.x), fmaf(rdir.y, ht, rpos.y), fmaf(rdir.z, ht, rpos.z));
           const f3 ns = PLAIN ? face_n : shading_normal(sc, tri, flags, face_n, hit);
           if (bounce == 0) { e0 = mb.x; e1 = mb.y; e2 = mb.z; }
-          const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.key0, rp.key1);
+          const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.keys);
           if (nE > 0) {
             const float u_pick = u16(rn.x >> 16), r1 = u16(rn.y >> 16), r2 = u16(rn.y & 0xffffu);
             const int li = pick_light(slight, nE, u_pick);
