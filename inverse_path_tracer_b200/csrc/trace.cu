@@ -136,14 +136,23 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays(DevScene sc, const float*
   __syncthreads();
   const long long n = n_live ? (long long)*n_live : (long long)n_direct;
   const long long total = n_live ? 2 * n : n;
-  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < total; m += (long long)gridDim.x * blockDim.x) {
-    const long long i = m < n ? m : (long long)cap + (m - n);
-    const float2* r2 = reinterpret_cast<const float2*>(rays + 6 * i);
-    const float2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2);
-    f3 p = mk3(a.x, a.y, b.x), d = mk3(b.y, c.x, c.y);
-    HitRec h = closest_hit_small(ss, p, d);
-    tri[i] = h.tri;
-    tout[i] = h.t;
+  // two rays per lane and trip (ray m and ray m + half) through the packed FP32x2 dual-ray loop of k_paths
+  const long long half = (total + 1) / 2;
+  const f3 zero3 = mk3(0.0f, 0.0f, 0.0f);
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < half; m += (long long)gridDim.x * blockDim.x) {
+    const long long m2 = m + half;
+    const bool two = m2 < total;
+    const long long i1 = m < n ? m : (long long)cap + (m - n);
+    const long long i2 = !two ? i1 : (m2 < n ? m2 : (long long)cap + (m2 - n));
+    const float2* r1 = reinterpret_cast<const float2*>(rays + 6 * i1);
+    const float2* r2 = reinterpret_cast<const float2*>(rays + 6 * i2);
+    const float2 a1 = __ldg(r1), b1 = __ldg(r1 + 1), c1 = __ldg(r1 + 2);
+    const float2 a2 = __ldg(r2), b2 = __ldg(r2 + 1), c2 = __ldg(r2 + 2);
+    HitRec h1, h2;
+    closest_hit_small2(ss, mk3(a1.x, a1.y, b1.x), mk3(b1.y, c1.x, c1.y), mk3(a2.x, a2.y, b2.x), two ? mk3(b2.y, c2.x, c2.y) : zero3, h1, h2);
+    tri[i1] = h1.tri;
+    tout[i1] = h1.t;
+    if (two) { tri[i2] = h2.tri; tout[i2] = h2.t; }
   }
 }
 
