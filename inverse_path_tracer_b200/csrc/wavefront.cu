@@ -103,8 +103,6 @@ __global__ void __launch_bounds__(kWfBlock, 4) k_wf_shade(DevScene sc, DevRender
   const f3 zero3 = mk3(0.0f, 0.0f, 0.0f);
   const unsigned lane = threadIdx.x & 31u;
   unsigned n_ext = 0, n_shadow = 0;
-  __shared__ int s_count[kWfBlock / 32];
-  __shared__ int s_block_base;
   for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
     const int j = base + (int)threadIdx.x;
     bool alive = j < n;
@@ -238,19 +236,15 @@ __global__ void __launch_bounds__(kWfBlock, 4) k_wf_shade(DevScene sc, DevRender
         lsamp[0 * cap + path] = L0; lsamp[1 * cap + path] = L1; lsamp[2 * cap + path] = L2;
       }
     }
-    // ---- append survivors: one atomic per BLOCK (every block of the grid adds to the same counter) ----
+    // ---- append survivors ----
     const unsigned amask = __ballot_sync(kFull, alive);
-    const int warp = (int)(threadIdx.x >> 5);
-    if (lane == 0) s_count[warp] = __popc(amask);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int total = 0;
-      for (int w = 0; w < kWfBlock / 32; w++) { const int c = s_count[w]; s_count[w] = total; total += c; }
-      s_block_base = total ? atomicAdd(n_out, total) : 0;
+    // one atomic per warp (one per block, through shared memory and three barriers per trip, measured no faster)
+    int basej = 0;
+    if (amask) {
+      const int leader = __ffs(amask) - 1;
+      if ((int)lane == leader) basej = atomicAdd(n_out, __popc(amask));
+      basej = __shfl_sync(kFull, basej, leader);
     }
-    __syncthreads();
-    const int basej = s_block_base + s_count[warp];
-    __syncthreads();   // the next trip of the loop rewrites s_count
     if (amask) {
       if (alive) {
         const size_t jn = (size_t)basej + __popc(amask & ((1u << lane) - 1u));
