@@ -110,8 +110,9 @@ int iptCreateGraphEx(void* scene, const IptRenderParams* p, const unsigned char*
                      unsigned long long* counters);
 /* raw edge sums of this shard only, left on the device (all-reduce them, then iptGraphCompress) */
 int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsigned char* target_dev, double* raw_dev, void* stream);
-/* DataWrapper::compress (inv_scene.h:87-115) on host arrays */
+/* DataWrapper::compress (inv_scene.h:87-115) on host arrays / on device arrays (same bits: the log is the canon's) */
 int iptGraphCompress(const double* raw, int n_triangles, float* data);
+int iptGraphCompressDevice(const double* raw_dev, int n_triangles, float* data_dev, void* stream);
 
 /* NEW (no reference counterpart): loss = sum over the shard of (L/(1+L) - target/255)^2 / (3*W*H) and
  * its gradient with respect to every diffuse albedo, nT*3 doubles.  max_depth is clamped to 64.  Exact for the

@@ -860,7 +860,7 @@ int iptGraphCompress(const double* raw, int nT, float* data) {
     float total = 0.0f;
     for (int src = 0; src < nT; src++) {
       const double* e = raw + ((size_t)dst * nT + src) * 16;
-      const float w = logf((float)e[1] + 1.0f);
+      const float w = canon_logf((float)e[1] + 1.0f);
       const float fs = (float)e[14];
       const float div = (fs != 0.0f) ? fs : 1.0f;
       row[src] = w;
@@ -872,6 +872,14 @@ int iptGraphCompress(const double* raw, int nT, float* data) {
     }
     for (int src = 0; src < nT; src++) weights[(size_t)dst * nT + src] = (total != 0.0f) ? row[src] / total : 0.0f;
   }
+  return 0;
+}
+
+int iptGraphCompressDevice(const double* raw_dev, int nT, float* data_dev, void* stream) {
+  if (!raw_dev || !data_dev || nT < 0) return fail("iptGraphCompressDevice: bad arguments");
+  if (nT == 0) return 0;
+  IPT_CUDA(launch_graph_compress(raw_dev, nT, data_dev, (cudaStream_t)stream));
+  g_launches += 1;
   return 0;
 }
 

@@ -32,6 +32,7 @@ cudaError_t launch_loss_dldpx(const float* img, const unsigned char* target, int
                               float* dldpx, double* loss, cudaStream_t st);
 cudaError_t launch_reduce_blocks(const float* block_acc, int n_blocks, int stride, double* out, int ints_from, int ints_per, cudaStream_t st);
 cudaError_t launch_set_kd(float4* mat, const float* kd, int nT, cudaStream_t st);
+cudaError_t launch_graph_compress(const double* raw, int nT, float* data, cudaStream_t st);
 cudaError_t launch_graph_finalize(const double* acc, const float4* mat, int nT, int n_edges, double* raw, cudaStream_t st);
 
 // BVH::build (bvh.h:109-205) over generic primitives.  nodes: 9 values per node

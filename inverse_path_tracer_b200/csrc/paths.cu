@@ -573,6 +573,34 @@ __global__ void k_graph_finalize(const double* __restrict__ acc, const float4* _
 }
 
 // albedo update from device memory: Kd and the load-time quotient Kd / pi (BSDF, path_trace.cu:15-17)
+// DataWrapper::compress (inv_scene.h:87-115) on the device: one thread per destination row (dst = 0..nT-1, then the
+// eye row), the row's weights summed in source order like the host version -- same operations, same bits
+__global__ void k_graph_compress(const double* __restrict__ raw, int nT, float* __restrict__ data) {
+  const int dst = blockIdx.x * blockDim.x + threadIdx.x;
+  if (dst > nT) return;
+  const size_t size = (size_t)(nT + 1) * nT;
+  float* weights = data;
+  float* pixels = data + size;
+  float* lights = data + 4 * size;
+  float total = 0.0f;
+  for (int src = 0; src < nT; src++) {
+    const double* e = raw + ((size_t)dst * nT + src) * 16;
+    const float w = canon_logf((float)e[1] + 1.0f);
+    const float fs = (float)e[14];
+    const float div = (fs != 0.0f) ? fs : 1.0f;
+    weights[(size_t)dst * nT + src] = w;
+    total += w;
+    for (int i = 0; i < 3; i++) {
+      pixels[((size_t)dst * nT + src) * 3 + i] = (float)e[2 + i] / div;
+      lights[((size_t)dst * nT + src) * 3 + i] = (float)e[8 + i] / div;
+    }
+  }
+  for (int src = 0; src < nT; src++) {
+    const float w = weights[(size_t)dst * nT + src];
+    weights[(size_t)dst * nT + src] = (total != 0.0f) ? w / total : 0.0f;
+  }
+}
+
 __global__ void k_set_kd(float4* __restrict__ mat, const float* __restrict__ kd, int nT) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nT) return;
@@ -667,6 +695,10 @@ cudaError_t launch_graph_finalize(const double* acc, const float4* mat, int nT, 
   return cudaGetLastError();
 }
 
+cudaError_t launch_graph_compress(const double* raw, int nT, float* data, cudaStream_t st) {
+  k_graph_compress<<<(nT + 1 + 127) / 128, 128, 0, st>>>(raw, nT, data);
+  return cudaGetLastError();
+}
 cudaError_t launch_set_kd(float4* mat, const float* kd, int nT, cudaStream_t st) {
   if (nT > 0) k_set_kd<<<(nT + 255) / 256, 256, 0, st>>>(mat, kd, nT);
   return cudaGetLastError();

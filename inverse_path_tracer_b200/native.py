@@ -33,7 +33,7 @@ EXPORTS = ["loadScene", "freeScene", "createImage", "createGraph", "getMaterials
            "iptGraphCompress", "iptRenderGrad", "iptRenderGradDevice", "iptSetMaterialsDevice", "iptBuildBVH",
            "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder", "iptTraceRaysStatsDevice",
            "iptSetIntegrator", "iptMeasureCopyGBps",
-           "iptSetBvhLargeTriangleLimit", "iptSceneLargeTriangles"]
+           "iptSetBvhLargeTriangleLimit", "iptSceneLargeTriangles", "iptGraphCompressDevice"]
 
 
 def lib():

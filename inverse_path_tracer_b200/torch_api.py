@@ -77,6 +77,19 @@ class TorchScene:
                           "iptGraphAccumulateDevice")
         return raw
 
+    def graph_data(self, p, target_u8, group=None, reduce=False):
+        """createGraph's data product on the device: (w [(nT+1), nT], pixel [(nT+1), nT, 3], light [(nT+1), nT, 3]), the
+        layout of ipt_cuda.generate_data (eye row last).  reduce=True sums the raw edge statistics over the row shards
+        of `group` first (DataWrapper::compress is not linear, so it runs after the all-reduce)."""
+        raw = self.graph_raw(p, target_u8)
+        if reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(raw, group=group)
+        n = (self.nT + 1) * self.nT
+        data = torch.empty(7 * n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            native._check(native.lib().iptGraphCompressDevice(_dp(raw), self.nT, _dp(data), _stream_ptr()), "iptGraphCompressDevice")
+        return (data[:n].view(self.nT + 1, self.nT), data[n:4 * n].view(self.nT + 1, self.nT, 3), data[4 * n:].view(self.nT + 1, self.nT, 3))
+
     def loss_and_grad(self, p, target_u8, out=None, img=None):
         """[loss, dLoss/dKd (nT*3)] float64 on the device for this row shard (sum over shards = whole image)"""
         assert target_u8.dtype == torch.uint8 and target_u8.is_cuda and target_u8.is_contiguous()

@@ -930,6 +930,12 @@ static double pow_exp2(double t) {
   memcpy(&s2, &b2, sizeof s2);
   return (p * s1) * s2;
 }
+// log of DataWrapper::compress through the same log2 kernel (host, device and oracle agree bit for bit)
+static float canon_logf(float x) {
+  if (!(x > 0.0f)) return x == 0.0f ? -INFINITY : NAN;
+  if (x == INFINITY) return x;
+  return (float)(pow_log2((double)x) * 0.69314718055994530942);
+}
 static float canon_pow(float x, float y) {
   if (y == 0.0f) return 1.0f;
   if (x != x || y != y) return x + y;
@@ -1246,7 +1252,7 @@ static void graph_compress(const std::vector<Edge>& edges, int nT, float* data) 
     std::vector<float> wrow(nT);
     for (int src = 0; src < nT; src++) {
       const Edge& e = edges[(size_t)dst * nT + src];
-      float w = logf((float)e.w_sum + 1.0f);
+      float w = canon_logf((float)e.w_sum + 1.0f);
       float div = ((float)e.factors_sum[0] != 0.0f) ? (float)e.factors_sum[0] : 1.0f;
       wrow[src] = w;
       w_total += w;
@@ -1268,6 +1274,7 @@ using namespace orc;
 
 extern "C" {
 float orc_canon_pow(float x, float y) { return orc::canon_pow(x, y); }
+float orc_canon_logf(float x) { return orc::canon_logf(x); }
 
 
 struct OrcParams {

@@ -507,3 +507,26 @@ def test_fuzz_scenes_bit_exact_all_integrators(ipt, oracle, chunk):
                 g.close()
     finally:
         ipt.set_integrator(0, 0)
+
+
+def test_graph_data_device_compress_equals_host(ipt, oracle):
+    """DataWrapper::compress on the device (torch front end: graph_data) against the host version on the same raw edge
+    sums: identical bits (the log of the edge weights is the canon's, not libm's), reference layout, rows sum to 1"""
+    import torch
+    from inverse_path_tracer_b200 import native
+    from inverse_path_tracer_b200.torch_api import TorchScene
+    ts = TorchScene(_scene0(oracle), asset_root=ASSETS, device=0)
+    target = torch.from_numpy(np.random.RandomState(4).randint(0, 256, (48, 64, 3)).astype(np.uint8)).cuda()
+    p = ipt.default_params(width=64, height=48, spp=8, seed=6)
+    raw = ts.graph_raw(p, target)
+    data = torch.empty(7 * (ts.nT + 1) * ts.nT, dtype=torch.float32, device="cuda")
+    import ctypes as C
+    native._check(native.lib().iptGraphCompressDevice(C.c_void_p(raw.data_ptr()), ts.nT, C.c_void_p(data.data_ptr()),
+                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "iptGraphCompressDevice")
+    host = native.graph_compress(raw.cpu().numpy(), ts.nT)
+    assert data.cpu().numpy().tobytes() == np.ascontiguousarray(host, np.float32).tobytes()
+    w, pixel, light = ts.graph_data(p, target)
+    assert w.shape == (ts.nT + 1, ts.nT) and pixel.shape == (ts.nT + 1, ts.nT, 3) and light.shape == (ts.nT + 1, ts.nT, 3)
+    sums = w.sum(-1).cpu().numpy()
+    assert all(abs(s - 1.0) < 1e-5 or s == 0.0 for s in sums) and sums[-1] > 0.99   # the eye row always sees something
+    ts.close()
