@@ -24,6 +24,11 @@ P_MIN = 1e-3   # ipt.py:26
 def build_graph(w, pixel, light=None):
     """ipt.py:67-82 on the (w, pixel, light) arrays of generate_data: returns (W [nT, nT], x [nT, 3]).
     W[dst, src] is the weight of edge src -> dst; rows whose weights are all below P_MIN stay zero."""
+    if torch.is_tensor(w):   # the device-resident product of TorchScene.graph_data: same steps, no host round trip
+        w = torch.where(w < P_MIN, torch.zeros_like(w), w).to(torch.float64)
+        s = w.sum(dim=-1, keepdim=True)
+        w = w / torch.where(s != 0, s, torch.ones_like(s))
+        return w[:-1].to(torch.float32), pixel[-1].to(torch.float32)
     w = np.array(w, np.float64, copy=True)
     w[w < P_MIN] = 0.0
     s = w.sum(axis=-1, keepdims=True)

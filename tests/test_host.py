@@ -241,6 +241,8 @@ def test_gcn_consumer_matches_edge_list_message_passing():
     assert float(W[3].abs().sum()) == 0.0
     rows = W.sum(-1)
     assert all(abs(float(r) - 1.0) < 1e-6 or float(r) == 0.0 for r in rows)
+    Wt, xt = gcn.build_graph(torch.tensor(w, dtype=torch.float32), torch.tensor(pixel, dtype=torch.float32), None)   # tensor inputs
+    assert torch.allclose(Wt, W, atol=1e-6) and torch.equal(xt, x)
     torch.manual_seed(0)
     layer = gcn.MPL(5, 7, None)
     h = torch.randn(nT, 5)
