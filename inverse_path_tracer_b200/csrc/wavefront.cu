@@ -25,7 +25,13 @@ namespace ipt {
 //   hits likewise at j and cap + j.
 // ------------------------------------------------------------------------------------------------
 enum { WF_END_AFTER = 1, WF_SH_VALID = 2, WF_EXT_VALID = 4 };
-constexpr int kWfBlock = 256;
+#ifndef IPT_WF_BLOCK
+#define IPT_WF_BLOCK 256
+#endif
+#ifndef IPT_WF_MINB
+#define IPT_WF_MINB 4
+#endif
+constexpr int kWfBlock = IPT_WF_BLOCK;
 
 struct WfBatch {
   int cap;          // slots per array
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(DevScene sc, DevRender
 // one bounce of shading for every live path: second half of directLighting of the previous bounce
 // ([D] of k_paths), then radiance() of this bounce's hit ([A] of k_paths); survivors are appended to the
 // next bounce's arrays
-__global__ void __launch_bounds__(kWfBlock, 4) k_wf_shade(DevScene sc, DevRender rp, WfBatch b, int bounce, const float4* __restrict__ sin_, float4* __restrict__ sout,
+__global__ void __launch_bounds__(kWfBlock, IPT_WF_MINB) k_wf_shade(DevScene sc, DevRender rp, WfBatch b, int bounce, const float4* __restrict__ sin_, float4* __restrict__ sout,
                                                        const float* __restrict__ rin, float* __restrict__ rout, const int* __restrict__ hit_tri,
                                                        const float* __restrict__ hit_t, const int* __restrict__ n_in, int* __restrict__ n_out,
                                                        float* __restrict__ lsamp, unsigned long long* __restrict__ counters) {
