@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   if (MODE == MODE_GRAD) vw = out.vstacks + ((size_t)(blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * (2 * out.vdepth) * 32 + lane) * 2;
   int vbuf = 0;                              // first slot of the half the path in flight records into
   int sw_buf = 0, sw_k = -1;                 // pending sweep: its half, next vertex to process (-1: none)
+  bool fin_wait = false;                     // a finished path waits for the pending sweep before it can be parked
   float pb0 = 0.0f, pb1 = 0.0f, pb2 = 0.0f;  // Pbar of the pending sweep
   float se0 = 0.0f, se1 = 0.0f, se2 = 0.0f;  // its path's L_e
   float sw0 = 0.0f, sw1 = 0.0f, sw2 = 0.0f;  // its pixel's dLoss/dL / spp
@@ -172,7 +173,10 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   auto finalize = [&]() {
     if (MODE == MODE_RENDER) { part0 += L0 * rp.inv_spp; part1 += L1 * rp.inv_spp; part2 += L2 * rp.inv_spp; }
     if (MODE == MODE_GRAD) {
-      while (sw_k >= 0) sweep_step();          // the previous path's sweep has not caught up: finish it here
+      // the previous path's sweep has not caught up (this path was shorter): finishing it here would run the sweep with
+      // one or two lanes of the warp (measured: 22 % of the sweep steps, half of the sweep's instructions), so the lane
+      // waits instead -- it starts no new sample until the shared per-trip steps below are through, then comes back here
+      if (sw_k >= 0) { fin_wait = true; return; }
       sw_buf = vbuf; vbuf = out.vdepth - vbuf;  // the next path records into the other half
       sw_k = min(path_len, out.vdepth) - 1;
       pb0 = pb1 = pb2 = 0.0f;
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     // A lane whose path is ending but still waits for its last shadow ray (end_after) may already start
     // the next sample of the SAME item; at an item boundary it idles one trip (once per 64 samples).
     {
-      const bool need = !ext_valid && !have_item && !exhausted && !end_after;
+      const bool need = !ext_valid && !have_item && !exhausted && !end_after && !(MODE == MODE_GRAD && fin_wait);
       const unsigned need_mask = __ballot_sync(kFull, need);
       if (need_mask) {
         const int leader = __ffs(need_mask) - 1;
@@ -379,7 +383,9 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         }
       }
     }
-    if (!ext_valid && have_item && s_next < s_end) {
+    // (adjoint: no new sample while a finished path waits for its slot, and no early start of the next sample while the
+    //  other stack half is still being swept -- the ending path will have to wait in it)
+    if (!ext_valid && have_item && s_next < s_end && !(MODE == MODE_GRAD && (fin_wait || (end_after && sw_k >= 0)))) {
       // camera ray (path_trace.cu:155-165, Ray::transform scene_basics.h:307-319)
       cur_s = s_next++;
       const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, 0u, IPT_STREAM_CAMERA, rp.keys);
@@ -457,9 +463,12 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       }
       if (end_after) {
         finalize();
-        // a sample started in [B] of this trip inherits clean accumulators (its multiplier is already 1)
-        L0 = L1 = L2 = 0.0f; e0 = e1 = e2 = 0.0f; d0 = d1 = d2 = 0.0f;
-        q0 = m0; q1 = m1; q2 = m2;
+        // a sample started in [B] of this trip inherits clean accumulators (its multiplier is already 1); a path that
+        // has to wait for its sweep slot started none, and its L_e is still needed when it is parked
+        if (!(MODE == MODE_GRAD && fin_wait)) {
+          L0 = L1 = L2 = 0.0f; e0 = e1 = e2 = 0.0f; d0 = d1 = d2 = 0.0f;
+          q0 = m0; q1 = m1; q2 = m2;
+        }
       }
     }
     if (MODE == MODE_GRAD) {
@@ -468,9 +477,10 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
 #pragma unroll 1
       for (int r = 0; r < kSweepPerTrip; r++) {
         const unsigned pending = __ballot_sync(kFull, sw_k >= 0);
-        if (__popc(pending) < kSweepQuorum) break;
+        if (__popc(pending) < kSweepQuorum && !__any_sync(kFull, fin_wait)) break;   // a waiting lane must make progress
         if (sw_k >= 0) sweep_step();
       }
+      if (fin_wait && sw_k < 0) { fin_wait = false; finalize(); }
     }
     active = ext_valid;
   }
