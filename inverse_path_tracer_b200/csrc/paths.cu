@@ -45,11 +45,11 @@ __device__ __forceinline__ int adj_light(const AdjVertex& v) { return __float_as
 // PLAIN is a compile-time promise that no triangle has per-vertex normals or a specular lobe (true for every
 // asset the reference ships); the Phong / vertex-normal code is then not compiled into the kernel at all.
 #ifndef IPT_SWEEP_PER_TRIP
-#define IPT_SWEEP_PER_TRIP 4
+#define IPT_SWEEP_PER_TRIP 3
 #endif
 constexpr int kSweepPerTrip = IPT_SWEEP_PER_TRIP;   // adjoint sweep: at most this many vertices per lane per trip of the main loop ...
 #ifndef IPT_SWEEP_QUORUM
-#define IPT_SWEEP_QUORUM 4
+#define IPT_SWEEP_QUORUM 1
 #endif
 constexpr int kSweepQuorum = IPT_SWEEP_QUORUM;      // ... while at least this many lanes of the warp have one pending
 template <int MODE, bool BVH, bool PLAIN>
