@@ -38,6 +38,10 @@ static std::mutex g_registry_mutex;
 static std::set<void*> g_registry;
 
 constexpr int kBruteForceMaxTris = 128;
+#ifndef IPT_LEAF_SIZE
+#define IPT_LEAF_SIZE 4
+#endif
+constexpr int kTraversalLeafSize = IPT_LEAF_SIZE;   // leaf size of the internal triangle tree (<= 7: three bits in a descriptor); 4 is the reference's rule
 constexpr double kBigTriangleDiag = 0.25;   // a triangle is "large" when its box diagonal exceeds this fraction of the scene's
 static int g_big_max = 128;                 // at most this many large triangles leave the tree (0: none)
 
@@ -323,7 +327,7 @@ static int upload_scene(SceneHandle* h) {
     std::vector<BvhNodeHost> nodes;
     std::vector<int> perm;
     std::string err;
-    if (nR && !build_bvh(boxes.data(), pos.data(), (int)nR, 4, &nodes, &perm, h->device, &err)) return fail("BVH build failed: " + err);
+    if (nR && !build_bvh(boxes.data(), pos.data(), (int)nR, kTraversalLeafSize, &nodes, &perm, h->device, &err)) return fail("BVH build failed: " + err);
     for (size_t j = 0; j < perm.size(); j++) perm[j] = rest[perm[j]];   // tree order -> triangle ids
     std::vector<float4> packed(2 * nodes.size());
     for (size_t i = 0; i < nodes.size(); i++) {
