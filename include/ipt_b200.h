@@ -146,7 +146,9 @@ int iptSceneLargeTriangles(void* scene);
 /* forward integrator for scenes traversed through the BVH: 0 = auto (wavefront), 1 = persistent megakernel
  * (the one brute-force scenes always use), 2 = wavefront: path state in device memory, one closest-hit
  * kernel per bounce over the compacted live paths.  `wavefront_slots` bounds the paths in flight per batch
- * (0 = default, 16 Mi).  All produce bit-identical images.  Applies to later render calls. */
+ * (0 = default, 16 Mi).  All produce bit-identical images.  Applies to later render calls.  The device-pointer
+ * render calls stay asynchronous with a bounded max_depth; with unbounded depth the wavefront reads the number of
+ * live paths back after every bounce (one stream synchronisation per bounce). */
 int iptSetIntegrator(int mode, int wavefront_slots);
 
 int iptWritePNG(const char* path, const unsigned char* rgb, int width, int height);
