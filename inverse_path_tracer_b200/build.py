@@ -79,5 +79,35 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines, sources=("paths.cu",)):
+    """Developer A/B build: lib/ab/<name>.so = the library with `sources` recompiled under extra -D flags
+    (select it with IPT_B200_LIB=...; tools/ab_variants.py).  The shipped library is not touched."""
+    build()
+    abdir = os.path.join(LIBDIR, "ab")
+    os.makedirs(abdir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        base = os.path.splitext(src)[0]
+        if src in sources:
+            obj = os.path.join(OBJDIR, "ab_%s_%s.o" % (name, base))
+            cmd = [nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout)
+                raise RuntimeError("nvcc failed on %s (%s)" % (src, name))
+            with open(os.path.join(abdir, name + ".ptxas.log"), "w") as f:
+                f.write(r.stdout)
+        else:
+            obj = os.path.join(OBJDIR, base + ".o")
+        objs.append(obj)
+    out = os.path.join(abdir, name + ".so")
+    r = subprocess.run([nvcc(), "-shared", "-o", out] + objs + ["-lz", "-gencode", "arch=compute_100a,code=sm_100a"],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("link failed (%s)" % name)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

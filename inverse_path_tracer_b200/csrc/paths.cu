@@ -44,6 +44,19 @@ __device__ __forceinline__ int adj_light(const AdjVertex& v) { return __float_as
 // addressing (a runtime choice between shared and global pointers forces generic loads)
 // PLAIN is a compile-time promise that no triangle has per-vertex normals or a specular lobe (true for every
 // asset the reference ships); the Phong / vertex-normal code is then not compiled into the kernel at all.
+// A/B switches of round 2 (profiles/r02_ab.txt): 1 = the shipped choice
+#ifndef IPT_FASTMATH
+#define IPT_FASTMATH 1        // sqrt / normalise through the single-test sequences of ipt_math.cuh (same bits as sqrtf and /)
+#endif
+#if IPT_FASTMATH
+#define IPT_NORMALIZE(v) normalize3_dev(v)
+#define IPT_SQRT_UNIT(x) sqrt_rn_unit(x)
+#define IPT_SQRT(x) sqrt_rn(x)
+#else
+#define IPT_NORMALIZE(v) normalize3(v)
+#define IPT_SQRT_UNIT(x) sqrtf(x)
+#define IPT_SQRT(x) sqrtf(x)
+#endif
 #ifndef IPT_SWEEP_PER_TRIP
 #define IPT_SWEEP_PER_TRIP 3
 #endif
@@ -101,7 +114,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   float m0 = 1.0f, m1 = 1.0f, m2 = 1.0f;     // multiplier
   float q0 = 1.0f, q1 = 1.0f, q2 = 1.0f;     // prevMultiplier
   float L0 = 0.0f, L1 = 0.0f, L2 = 0.0f;
-  float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;     // L_e (sticky, path_trace.cu:168)
+  int e_tri = -1;                            // L_e (sticky, path_trace.cu:168) = Ke of the path's first hit, kept as that triangle's index
   float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;     // L_d (sticky on a miss)
   int bounce = 0;
   // graph mode
@@ -121,10 +134,22 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   float sw0 = 0.0f, sw1 = 0.0f, sw2 = 0.0f;  // its pixel's dLoss/dL / spp
   float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;     // dLoss/dL_pixel / spp of the item's pixel
   int path_len = 0;                          // vertices recorded for the path being finalised
-  unsigned long long n_paths = 0, n_ext = 0, n_shadow = 0;
+  unsigned n_paths = 0, n_ext = 0, n_shadow = 0;   // per lane and launch: < 2^32 (a lane traces ~10^5 rays per second of launch)
+  // the light connection of the current bounce; written in [A] and read in [C] / [D] only when sh_valid, so they are
+  // not reset per trip (the resets were ~30 register moves per trip at full warp width)
+  f3 sh_org = zero3, sh_dir = zero3;
+  int sh_light = -1, sh_tri = -1;
+  float sh_cos = 0.0f, sh_pt = 1.0f, sh_gw = 0.0f;
+  float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;   // BSDF(isDirect = true) of this bounce
 
   // 1/p_sample/p_RR/(1-P_SPEC) in double then rounded (inv_path_trace.cu:145)
   const float gscale = (float)(1.0 / (double)IPT_INV_PI_F / (double)rp.p_rr / 1.0);
+
+  // L_e of the path in flight: the emission record of its first hit (zero before that and for non-emitters)
+  auto load_le = [&](float& e0, float& e1, float& e2) {
+    e0 = e1 = e2 = 0.0f;
+    if (e_tri >= 0) { const float4 ke = mat[1 * nT + e_tri]; e0 = ke.x; e1 = ke.y; e2 = ke.z; }
+  };
 
   // one vertex of a pending adjoint sweep: Pbar_k = C_k + Kd_k b_k Pbar_{k+1}.
   // The sweep of a finished path is not run where the path ends (there ~2 lanes of a warp would walk their
@@ -180,7 +205,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       sw_buf = vbuf; vbuf = out.vdepth - vbuf;  // the next path records into the other half
       sw_k = min(path_len, out.vdepth) - 1;
       pb0 = pb1 = pb2 = 0.0f;
-      se0 = e0; se1 = e1; se2 = e2;
+      load_le(se0, se1, se2);
       sw0 = w0; sw1 = w1; sw2 = w2;
     }
     fin_left--;
@@ -199,14 +224,10 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     // (one radiance() call, path_trace.cu:111-144 / inv_path_trace.cu:109-150; the contribution
     //  prevMultiplier * (L_e + L_d) is applied in [D] once this bounce's shadow ray is resolved)
     bool ext_valid = false, sh_valid = false, end_after = false;
-    f3 sh_org = zero3, sh_dir = zero3;
-    int sh_light = -1, sh_tri = -1;
-    float sh_cos = 0.0f, sh_pt = 1.0f, sh_gw = 0.0f;
-    float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;   // BSDF(isDirect = true) of this bounce
     if (active) {
       if (h.tri < 0) {
         // miss (path_trace.cu:116): the stale L_e / L_d are re-added with the new multiplier
-        if (MODE != MODE_GRAPH) { L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2); }
+        if (MODE != MODE_GRAPH) { float e0, e1, e2; load_le(e0, e1, e2); L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2); }
         if (MODE == MODE_GRAD) {
           if (bounce < out.vdepth) { float4* vp = vw + (size_t)(vbuf + bounce) * 64; vp[0] = make_float4(__int_as_float(-1), 0.0f, __int_as_float(-1), 0.0f); vp[1] = make_float4(q0, q1, q2, 0.0f); }
           path_len = bounce + 1;
@@ -219,7 +240,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         const f3 face_n = xyz(mat[3 * nT + tri]);
         const f3 hit = mk3(fmaf(rdir.x, h.t, rpos.x), fmaf(rdir.y, h.t, rpos.y), fmaf(rdir.z, h.t, rpos.z));
         const f3 ns = PLAIN ? face_n : shading_normal(sc, tri, flags, face_n, hit);
-        if (MODE != MODE_GRAPH && bounce == 0) { e0 = mb.x; e1 = mb.y; e2 = mb.z; }
+        if (MODE != MODE_GRAPH && bounce == 0) e_tri = tri;
         const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.keys);
         AdjVertex vx;
         if (MODE == MODE_GRAD) { vx.a = make_float4(__int_as_float(tri), 0.0f, __int_as_float(-1), 0.0f); vx.p = make_float4(q0, q1, q2, 0.0f); }
@@ -251,23 +272,22 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
           const float u_pick = u16(rn.x >> 16), r1 = u16(rn.y >> 16), r2 = u16(rn.y & 0xffffu);
           const int li = pick_light(slight, nE, u_pick);
           const float4 la = slight[3 * li], lb = slight[3 * li + 1], lc = slight[3 * li + 2];
-          const float sq = sqrtf(r1);
+          const float sq = IPT_SQRT_UNIT(r1);   // r1 in [2^-17, 1)
           const float c1 = 1.0f - sq, c2 = sq * (1.0f - r2), c3 = r2 * sq;
           const f3 ep = mk3(fmaf(c3, lc.x, fmaf(c2, lb.x, c1 * la.x)), fmaf(c3, lc.y, fmaf(c2, lb.y, c1 * la.y)), fmaf(c3, lc.z, fmaf(c2, lb.z, c1 * la.z)));
-          const f3 toLight = normalize3(ep - hit);
+          const f3 toLight = IPT_NORMALIZE(ep - hit);
           const float cos_theta = dot3(ns, toLight);
-          if (!(cos_theta < 0.0f)) {
-            sh_valid = true;
-            sh_org = hit; sh_dir = toLight;
-            sh_light = __float_as_int(lc.w); sh_tri = tri;
-            sh_cos = cos_theta; sh_pt = lb.w; sh_gw = gweight;
-            if (MODE != MODE_GRAPH) {
-              f0 = ma.x; f1 = ma.y; f2 = ma.z;   // BSDF(isDirect = true): Kd, no 1/pi (path_trace.cu:14-17)
-              if (!PLAIN && (flags & TRI_ANY_KS)) {
-                const float4 mc = mat[4 * nT + tri];
-                const float co = phong_coeff(ns, rdir, toLight, ma.w);
-                f0 = fmaf(mc.x, co, f0); f1 = fmaf(mc.y, co, f1); f2 = fmaf(mc.z, co, f2);
-              }
+          // written unconditionally (plain register definitions, no predicated copies); only read when sh_valid
+          sh_valid = !(cos_theta < 0.0f);
+          sh_org = hit; sh_dir = toLight;
+          sh_light = __float_as_int(lc.w); sh_tri = tri;
+          sh_cos = cos_theta; sh_pt = lb.w; sh_gw = gweight;
+          if (MODE != MODE_GRAPH && !PLAIN) {   // (plain scenes: BSDF(isDirect) is Kd of sh_tri, re-read in [D])
+            f0 = ma.x; f1 = ma.y; f2 = ma.z;   // BSDF(isDirect = true): Kd, no 1/pi (path_trace.cu:14-17)
+            if (sh_valid && (flags & TRI_ANY_KS)) {
+              const float4 mc = mat[4 * nT + tri];
+              const float co = phong_coeff(ns, rdir, toLight, ma.w);
+              f0 = fmaf(mc.x, co, f0); f1 = fmaf(mc.y, co, f1); f2 = fmaf(mc.z, co, f2);
             }
           }
         }
@@ -285,7 +305,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
             float sphi, cphi;
             sincos2pi(u01(rn.z), &sphi, &cphi);
             const float ut = u01(rn.w);
-            const float cth = sqrtf(ut), sth = sqrtf(1.0f - ut);
+            const float cth = IPT_SQRT_UNIT(ut), sth = IPT_SQRT(1.0f - ut);   // ut in [2^-33, 1]; 1 - ut may be 0
             const f3 hemi = mk3(sth * cphi, sth * sphi, cth);
             if (flags & TRI_NEG_Z) {
               nd = -hemi;
@@ -293,7 +313,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
               const float4 r0 = mat[5 * nT + tri], r1 = mat[6 * nT + tri], r2 = mat[7 * nT + tri];
               nd = mk3(dot3(r0.x, r0.y, r0.z, hemi), dot3(r1.x, r1.y, r1.z, hemi), dot3(r2.x, r2.y, r2.z, hemi));
             }
-            nd = normalize3(nd);
+            nd = IPT_NORMALIZE(nd);
           }
           const float cosn = dot3(nd, ns);
           if (MODE == MODE_GRAPH) {
@@ -328,6 +348,8 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
           // no light connection to wait for: L_d = 0, apply this bounce's contribution now
           d0 = d1 = d2 = 0.0f;
           if (MODE != MODE_GRAPH) {
+            float e0, e1, e2;
+            load_le(e0, e1, e2);
             L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2);
             q0 = m0; q1 = m1; q2 = m2;
           }
@@ -393,12 +415,12 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       const float y = fmaf(pix_r + u01(rn.y), -rp.two_over_h, 1.0f);
       const f3 dl = mk3(x, y, 1.0f);
       rpos = mk3(sc.cam[3], sc.cam[7], sc.cam[11]);
-      rdir = normalize3(mk3(dot3(sc.cam[0], sc.cam[1], sc.cam[2], dl), dot3(sc.cam[4], sc.cam[5], sc.cam[6], dl), dot3(sc.cam[8], sc.cam[9], sc.cam[10], dl)));
+      rdir = IPT_NORMALIZE(mk3(dot3(sc.cam[0], sc.cam[1], sc.cam[2], dl), dot3(sc.cam[4], sc.cam[5], sc.cam[6], dl), dot3(sc.cam[8], sc.cam[9], sc.cam[10], dl)));
       m0 = m1 = m2 = 1.0f;
       bounce = 0;
       gweight = 1.0f;
       gdst = nT;
-      if (!end_after) { q0 = q1 = q2 = 1.0f; L0 = L1 = L2 = 0.0f; e0 = e1 = e2 = 0.0f; d0 = d1 = d2 = 0.0f; }
+      if (!end_after) { q0 = q1 = q2 = 1.0f; L0 = L1 = L2 = 0.0f; e_tri = -1; d0 = d1 = d2 = 0.0f; }
       ext_valid = true;
       n_paths++;
     }
@@ -407,11 +429,11 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     // =========== [C] closest hits: extension ray and shadow ray ==========================================
     HitRec hs;
     if (!BVH) {
-      closest_hit_small2(ss, rpos, ext_valid ? rdir : zero3, sh_org, sh_dir, h, hs);
+      closest_hit_small2(ss, rpos, ext_valid ? rdir : zero3, sh_org, sh_valid ? sh_dir : zero3, h, hs);
     } else {
       h.t = INFINITY; h.tri = -1;
       hs.t = INFINITY; hs.tri = -1;
-      if (ss.nGroups > 0) closest_hit_small2(ss, rpos, ext_valid ? rdir : zero3, sh_org, sh_dir, h, hs);
+      if (ss.nGroups > 0) closest_hit_small2(ss, rpos, ext_valid ? rdir : zero3, sh_org, sh_valid ? sh_dir : zero3, h, hs);
       if (ext_valid) h = closest_hit_bvh(sc, rpos, rdir, bvh_stack, h);
       if (sh_valid) hs = closest_hit_bvh(sc, sh_org, sh_dir, bvh_stack, hs);
     }
@@ -448,6 +470,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
             }
           } else {
             const float g = (sh_cos * cos_tp) / ((hs.t * hs.t) * sh_pt);
+            if (PLAIN) { const float4 kd = mat[sh_tri]; f0 = kd.x; f1 = kd.y; f2 = kd.z; }   // BSDF(isDirect = true) = Kd (path_trace.cu:14-17)
             d0 = f0 * (lmb.x * g); d1 = f1 * (lmb.y * g); d2 = f2 * (lmb.z * g);
             if (MODE == MODE_GRAD) {
               const int k = path_len - 1;   // the vertex recorded in [A] of this trip
@@ -458,6 +481,8 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       }
       if (MODE != MODE_GRAPH) {
         // renderSample loop body (path_trace.cu:176-180)
+        float e0, e1, e2;
+        load_le(e0, e1, e2);
         L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2);
         q0 = m0; q1 = m1; q2 = m2;
       }
@@ -466,7 +491,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         // a sample started in [B] of this trip inherits clean accumulators (its multiplier is already 1); a path that
         // has to wait for its sweep slot started none, and its L_e is still needed when it is parked
         if (!(MODE == MODE_GRAD && fin_wait)) {
-          L0 = L1 = L2 = 0.0f; e0 = e1 = e2 = 0.0f; d0 = d1 = d2 = 0.0f;
+          L0 = L1 = L2 = 0.0f; e_tri = -1; d0 = d1 = d2 = 0.0f;
           q0 = m0; q1 = m1; q2 = m2;
         }
       }
@@ -489,15 +514,16 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   }
 
   // ---- epilogue: counters + per-block accumulators --------------------------------------------------
+  unsigned long long w_paths = n_paths, w_ext = n_ext, w_shadow = n_shadow;
   for (int o = 16; o > 0; o >>= 1) {
-    n_paths += __shfl_down_sync(kFull, n_paths, o);
-    n_ext += __shfl_down_sync(kFull, n_ext, o);
-    n_shadow += __shfl_down_sync(kFull, n_shadow, o);
+    w_paths += __shfl_down_sync(kFull, w_paths, o);
+    w_ext += __shfl_down_sync(kFull, w_ext, o);
+    w_shadow += __shfl_down_sync(kFull, w_shadow, o);
   }
   if (lane == 0 && out.counters) {
-    atomicAdd(out.counters + 0, n_paths);
-    atomicAdd(out.counters + 1, n_ext);
-    atomicAdd(out.counters + 2, n_shadow);
+    atomicAdd(out.counters + 0, w_paths);
+    atomicAdd(out.counters + 1, w_ext);
+    atomicAdd(out.counters + 2, w_shadow);
   }
   if (MODE != MODE_RENDER && out.acc_in_smem == 1) {
     __syncthreads();

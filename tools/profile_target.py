@@ -25,11 +25,14 @@ ap.add_argument("--mode", default="render")
 ap.add_argument("--traversal", type=int, default=0)
 ap.add_argument("--group", type=int, default=-1)
 ap.add_argument("--row-step", type=int, default=1)
+ap.add_argument("--integrator", type=int, default=0, help="BVH scenes: 0 auto, 1 megakernel, 2 wavefront")
 a = ap.parse_args()
 if a.scene == "cornell":
     objs = [{"pos": [0, 0, 4], "ori": [0, 0, 0], "scl": [2, 2, 2], "obj": "./CornellBox/CornellBox-Empty-CO.obj", "mtl": "./CornellBox/CornellBox-Empty-CO.mtl"}]
 else:
     objs = parse_scene_file(os.path.join(ASSETS, "scenes", "0.txt"))
+if a.integrator:
+    ipt.set_integrator(a.integrator)
 sc = ipt.Scene(objs, asset_root=ASSETS, traversal_mode=a.traversal)
 rng = np.random.RandomState(0)
 target = rng.randint(0, 256, (a.size, a.size, 3)).astype(np.uint8)
