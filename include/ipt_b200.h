@@ -74,7 +74,10 @@ int iptSetAssetRoot(const char* root);
 /* CUDA device used by scenes loaded afterwards from this thread (default -1: current device).
  * -2 loads host-only handles (loader tables, get/setMaterials); every compute call on them fails. */
 int iptSetDevice(int device);
-/* 0 = auto (brute force up to 128 triangles, BVH above), 1 = force brute force, 2 = force BVH */
+/* 0 = auto (brute force up to 128 triangles, BVH above), 1 = force brute force, 2 = force BVH.
+ * Like iptSetDevice, iptSetBvhLargeTriangleLimit and iptSetIntegrator this is a setting of the CALLING THREAD that
+ * loadScene copies into the handle: a loaded scene keeps the settings it was loaded under, so threads that drive
+ * different scenes (eight scenes on eight GPUs from one process) do not interfere. */
 int iptSetTraversalMode(int mode);
 
 int iptSceneInfo(void* scene, int* n_triangles, int* n_emissives, int* n_objects, int* n_bvh_nodes, int* uses_bvh);
@@ -146,10 +149,12 @@ int iptSceneLargeTriangles(void* scene);
 /* forward integrator for scenes traversed through the BVH: 0 = auto (wavefront), 1 = persistent megakernel
  * (the one brute-force scenes always use), 2 = wavefront: path state in device memory, one closest-hit
  * kernel per bounce over the compacted live paths.  `wavefront_slots` bounds the paths in flight per batch
- * (0 = default, 16 Mi).  All produce bit-identical images.  Applies to later render calls.  The device-pointer
- * render calls stay asynchronous with a bounded max_depth; with unbounded depth the wavefront reads the number of
- * live paths back after every bounce (one stream synchronisation per bounce). */
+ * (0 = default, 16 Mi).  All produce bit-identical images.  iptSetIntegrator sets the calling thread's default for
+ * scenes loaded afterwards; iptSceneSetIntegrator changes one loaded scene (later render calls on it).  The
+ * device-pointer render calls stay asynchronous with a bounded max_depth; with unbounded depth the wavefront reads
+ * the number of live paths back after every bounce (one stream synchronisation per bounce). */
 int iptSetIntegrator(int mode, int wavefront_slots);
+int iptSceneSetIntegrator(void* scene, int mode, int wavefront_slots);
 
 int iptWritePNG(const char* path, const unsigned char* rgb, int width, int height);
 int iptReadPNG(const char* path, unsigned char* rgb, int capacity_bytes, int* width, int* height);

@@ -22,7 +22,7 @@
 #include "../../include/ipt_b200.h"
 #include "device_scene.h"
 #include "kernels.h"
-#include "scene_host.h"
+#include "scene_handle.h"
 #include "ipt_math.cuh"
 
 namespace ipt {
@@ -30,10 +30,13 @@ namespace ipt {
 static thread_local std::string g_error;
 static std::string g_asset_root;
 static thread_local int g_device = -1;
-static int g_traversal_mode = 0;
-static int g_integrator = 0;          // 0 auto, 1 megakernel, 2 wavefront (BVH scenes)
-static int g_wf_slots = 1 << 24;
-static std::atomic<unsigned long long> g_launches(0);
+// Loader / integrator knobs are per calling thread and are copied into the handle by loadScene(): a scene keeps the
+// settings it was loaded under (and iptSceneSetIntegrator changes one scene), so threads driving different scenes --
+// eight scenes on eight GPUs from one process -- cannot disturb each other.
+static thread_local int g_traversal_mode = 0;
+static thread_local int g_integrator = 0;          // 0 auto, 1 megakernel, 2 wavefront (BVH scenes)
+static thread_local int g_wf_slots = 1 << 24;
+std::atomic<unsigned long long> g_launches(0);
 static std::mutex g_registry_mutex;
 static std::set<void*> g_registry;
 
@@ -43,94 +46,20 @@ constexpr int kBruteForceMaxTris = 128;
 #endif
 constexpr int kTraversalLeafSize = IPT_LEAF_SIZE;   // leaf size of the internal triangle tree (<= 7: three bits in a descriptor); 4 is the reference's rule
 constexpr double kBigTriangleDiag = 0.25;   // a triangle is "large" when its box diagonal exceeds this fraction of the scene's
-static int g_big_max = 128;                 // at most this many large triangles leave the tree (0: none)
+static thread_local int g_big_max = 128;    // at most this many large triangles leave the tree (0: none)
 
-static int fail(const std::string& msg) {
+int fail(const std::string& msg) {
   g_error = msg;
   return -1;
 }
-#define IPT_CUDA(call)                                                                                        \
-  do {                                                                                                        \
-    cudaError_t e__ = (call);                                                                                 \
-    if (e__ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e__));                 \
-  } while (0)
 
-struct Scratch {
-  void* ptr = nullptr;
-  size_t bytes = 0;
-  cudaError_t reserve(size_t need) {
-    if (need <= bytes) return cudaSuccess;
-    if (ptr) cudaFree(ptr);
-    ptr = nullptr;
-    bytes = 0;
-    cudaError_t e = cudaMalloc(&ptr, need);
-    if (e == cudaSuccess) bytes = need;
-    return e;
-  }
-  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
-};
-
-struct SceneHandle {
-  HostScene host;
-  int device = 0;
-  int sm_count = 0;
-  cudaStream_t stream = nullptr;
-  float4* geom = nullptr;
-  float4* planes = nullptr;
-  int2* grange = nullptr;
-  float4* slot_edges = nullptr;
-  int2* slot_tri = nullptr;
-  int n_groups = 0;
-  int n_slots = 0;
-  float4* mat = nullptr;
-  float4* light = nullptr;
-  float4* vtx = nullptr;
-  float4* bvh_nodes = nullptr;
-  float4* bvh_wide = nullptr;
-  int bvh_root_desc = 0;
-  int bvh_depth = 1;
-  int* bvh_prims = nullptr;
-  int n_nodes = 0;
-  int n_big = 0;
-  bool use_bvh = false;
-  bool host_only = false;
-  // ring of CUDA event pairs bracketing the last kEventRing k_paths launches (roofline timing without
-  // synchronising inside a timed loop)
-  static constexpr int kEventRing = 64;
-  cudaEvent_t ev_start[kEventRing] = {}, ev_stop[kEventRing] = {};
-  unsigned long long ev_count = 0;   // loaded with iptSetDevice(-2): tables only, no device arrays
-  int* host_live = nullptr;          // pinned word for the wavefront integrator's live count
-  Scratch wavefront;
-  Scratch partial, counters, cnt_out, trace_counter, block_acc, vstacks, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
-  std::mutex mutex;
-
-  DevScene dev() const {
-    DevScene d;
-    d.geom = geom; d.planes = planes; d.grange = grange; d.slot_edges = slot_edges; d.slot_tri = slot_tri; d.nGroups = n_groups; d.nSlots = n_slots; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
-    d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.nBig = n_big; d.use_bvh = use_bvh ? 1 : 0; d.plain = (!host.any_vn && !host.any_specular) ? 1 : 0;
-    memcpy(d.cam, host.cam, sizeof(d.cam));
-    return d;
-  }
-  void destroy() {
-    if (host_only) return;
-    cudaSetDevice(device);
-    if (stream) cudaStreamSynchronize(stream);
-    cudaFree(geom); cudaFree(planes); cudaFree(grange); cudaFree(slot_edges); cudaFree(slot_tri); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_wide); cudaFree(bvh_prims);
-    Scratch* all[] = {&wavefront, &partial, &counters, &cnt_out, &trace_counter, &block_acc, &vstacks, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
-    for (Scratch* s : all) s->release();
-    if (host_live) cudaFreeHost(host_live);
-    if (stream) cudaStreamDestroy(stream);
-    for (int i = 0; i < kEventRing; i++) { if (ev_start[i]) cudaEventDestroy(ev_start[i]); if (ev_stop[i]) cudaEventDestroy(ev_stop[i]); }
-  }
-};
-
-static SceneHandle* checked(void* p) {
+SceneHandle* checked(void* p) {
   std::lock_guard<std::mutex> lk(g_registry_mutex);
   if (!p || !g_registry.count(p)) { g_error = "invalid scene handle"; return nullptr; }
   return (SceneHandle*)p;
 }
 // compute entry points: the scene must live on a GPU (there is no CPU fallback)
-static SceneHandle* checked_device(void* p) {
+SceneHandle* checked_device(void* p) {
   SceneHandle* h = checked(p);
   if (h && h->host_only) { g_error = "scene was loaded host-only (iptSetDevice(-2)); compute needs a CUDA device"; return nullptr; }
   return h;
@@ -263,7 +192,7 @@ static int upload_scene(SceneHandle* h) {
   }
   IPT_CUDA(cudaMemcpy(h->light, light.data(), light.size() * sizeof(float4), cudaMemcpyHostToDevice));
 
-  h->use_bvh = (g_traversal_mode == 2) || (g_traversal_mode == 0 && (int)nT > kBruteForceMaxTris);
+  h->use_bvh = (h->traversal_mode == 2) || (h->traversal_mode == 0 && (int)nT > kBruteForceMaxTris);
   // the brute-force set: every triangle of a small scene; in a BVH scene the few triangles that are large against
   // the scene (room walls around a dense mesh).  Left in the tree, a large triangle inflates the boxes of every
   // node above its leaf and rays far from the mesh descend deep for nothing; outside it the tree stays tight and
@@ -272,7 +201,7 @@ static int upload_scene(SceneHandle* h) {
   std::vector<int> brute, rest;
   if (!h->use_bvh) {
     for (size_t i = 0; i < nT; i++) brute.push_back((int)i);
-  } else if ((int)nT > kBruteForceMaxTris && g_big_max > 0) {
+  } else if ((int)nT > kBruteForceMaxTris && h->big_max > 0) {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (size_t i = 0; i < nT; i++)
       for (int j = 0; j < 3; j++)
@@ -289,7 +218,7 @@ static int upload_scene(SceneHandle* h) {
       if (d2 > kBigTriangleDiag * kBigTriangleDiag * scene_diag2) cand.push_back(std::make_pair(-d2, (int)i));
     }
     std::sort(cand.begin(), cand.end());
-    if ((int)cand.size() > g_big_max) cand.resize(g_big_max);
+    if ((int)cand.size() > h->big_max) cand.resize(h->big_max);
     std::vector<char> is_big(nT, 0);
     for (size_t c = 0; c < cand.size(); c++) is_big[cand[c].second] = 1;
     for (size_t i = 0; i < nT; i++) (is_big[i] ? brute : rest).push_back((int)i);
@@ -300,16 +229,22 @@ static int upload_scene(SceneHandle* h) {
     std::vector<float4> planes, edges;
     std::vector<int2> grange, slot_tri;
     build_plane_groups(hs, brute, &planes, &grange, &edges, &slot_tri);
+    // the kernels walk the set as one record stream (device_scene.h): {plane}{meta} per group, 5 edges + ids per slot
+    std::vector<float4> stream;
+    auto ibits = [](int v) { float f; memcpy(&f, &v, 4); return f; };
+    for (size_t g = 0; g < planes.size(); g++) {
+      const int ns = grange[g].y - grange[g].x;
+      stream.push_back(planes[g]);
+      stream.push_back(make_float4(ibits((2 + 6 * ns) * (int)sizeof(float4)), 0.0f, 0.0f, 0.0f));
+      for (int j = grange[g].x; j < grange[g].y; j++) {
+        for (int k = 0; k < 5; k++) stream.push_back(edges[5 * (size_t)j + k]);
+        stream.push_back(make_float4(ibits(slot_tri[j].x), ibits(slot_tri[j].y), 0.0f, 0.0f));
+      }
+    }
     h->n_groups = (int)planes.size();
-    h->n_slots = (int)slot_tri.size();
-    IPT_CUDA(cudaMalloc(&h->planes, planes.size() * sizeof(float4)));
-    IPT_CUDA(cudaMalloc(&h->grange, grange.size() * sizeof(int2)));
-    IPT_CUDA(cudaMalloc(&h->slot_edges, edges.size() * sizeof(float4)));
-    IPT_CUDA(cudaMalloc(&h->slot_tri, slot_tri.size() * sizeof(int2)));
-    IPT_CUDA(cudaMemcpy(h->planes, planes.data(), planes.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    IPT_CUDA(cudaMemcpy(h->grange, grange.data(), grange.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    IPT_CUDA(cudaMemcpy(h->slot_edges, edges.data(), edges.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    IPT_CUDA(cudaMemcpy(h->slot_tri, slot_tri.data(), slot_tri.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    h->n_stream = (int)stream.size();
+    IPT_CUDA(cudaMalloc(&h->bf_stream, stream.size() * sizeof(float4)));
+    IPT_CUDA(cudaMemcpy(h->bf_stream, stream.data(), stream.size() * sizeof(float4), cudaMemcpyHostToDevice));
   }
   if (h->use_bvh && nT) {
     // triangle-level tree: box = vertex bounds, split position = triangle center (the analogue of
@@ -393,12 +328,7 @@ static int upload_scene(SceneHandle* h) {
   return 0;
 }
 
-struct Plan {
-  DevRender rp;
-  int rows;
-};
-
-static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan) {
+int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan) {
   (void)h;
   if (!p) return fail("null render params");
   if (p->width <= 0 || p->height <= 0 || p->spp <= 0) return fail("width, height and spp must be positive");
@@ -423,6 +353,9 @@ static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan)
   }
   rp.group_samples = (gs <= 0 || gs > p->spp) ? p->spp : gs;
   rp.groups = (p->spp + rp.group_samples - 1) / rp.group_samples;
+  // the kernels index work items (pixel, group) in 32 bits
+  if ((long long)p->width * p->height * rp.groups >= (1ll << 31) - (1ll << 24))
+    return fail("too many work items (width * height * ceil(spp / group_samples) must stay below 2^31): render row shards or use larger sample groups");
   const int step = p->row_step < 1 ? 1 : p->row_step;
   const int rows = (re - rb + step - 1) / step;
   rp.row_begin = rb;
@@ -437,7 +370,7 @@ static int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan)
   return 0;
 }
 
-static int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev,
+int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev,
                           cudaStream_t st) {
   const DevScene sc = h->dev();
   const DevRender& rp = plan.rp;
@@ -448,13 +381,13 @@ static int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsi
   if (counters_dev) IPT_CUDA(cudaMemsetAsync(counters_dev, 0, 3 * sizeof(unsigned long long), st));
   DevOut out;
   memset(&out, 0, sizeof(out));
-  out.work_counter = ctr + 4;
+  out.work_counter = reinterpret_cast<unsigned*>(ctr + 4);
   out.counters = counters_dev ? counters_dev : ctr;
   out.partial = (float*)h->partial.ptr;
-  if (sc.use_bvh && g_integrator != 1) {
+  if ((sc.use_bvh && h->integrator != 1) || (!sc.use_bvh && h->integrator == 2)) {
     // large scenes: wavefront (wavefront.cu); batches of at most `cap` paths
     const long long total = (long long)rp.n_pix * std::min(rp.spp, rp.group_samples);
-    const int cap = (int)std::max<long long>(1, std::min<long long>(total, (long long)g_wf_slots));
+    const int cap = (int)std::max<long long>(1, std::min<long long>(total, (long long)h->wf_slots));
     IPT_CUDA(h->wavefront.reserve(wavefront_workspace_bytes(cap)));
     if (!h->host_live) IPT_CUDA(cudaHostAlloc((void**)&h->host_live, sizeof(int), cudaHostAllocDefault));
     const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
@@ -521,6 +454,16 @@ int iptSetIntegrator(int mode, int wavefront_slots) {
   g_wf_slots = wavefront_slots > 0 ? wavefront_slots : (1 << 24);
   return 0;
 }
+int iptSceneSetIntegrator(void* scene, int mode, int wavefront_slots) {
+  SceneHandle* h = checked(scene);
+  if (!h) return -1;
+  if (mode < 0 || mode > 2) return fail("integrator must be 0, 1 or 2");
+  if (wavefront_slots < 0) return fail("wavefront_slots must be >= 0");
+  std::lock_guard<std::mutex> lk(h->mutex);
+  h->integrator = mode;
+  h->wf_slots = wavefront_slots > 0 ? wavefront_slots : (1 << 24);
+  return 0;
+}
 int iptSetTraversalMode(int mode) {
   if (mode < 0 || mode > 2) return fail("traversal mode must be 0, 1 or 2");
   g_traversal_mode = mode;
@@ -567,6 +510,7 @@ int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mt
   if (scenePtr) *scenePtr = nullptr;
   if (!scenePtr || n < 0 || (n > 0 && (!poss || !oris || !scls || !obj_fs || !mtl_fs))) { fail("loadScene: bad arguments"); return 0; }
   SceneHandle* h = new SceneHandle();
+  h->traversal_mode = g_traversal_mode; h->big_max = g_big_max; h->integrator = g_integrator; h->wf_slots = g_wf_slots;
   std::string err;
   if (!build_host_scene(poss, oris, scls, obj_fs, mtl_fs, n, g_asset_root, &h->host, &err)) {
     fprintf(stderr, "ipt_b200: loadScene failed: %s\n", err.c_str());
@@ -814,7 +758,7 @@ int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsign
   IPT_CUDA(cudaMemsetAsync(h->acc.ptr, 0, (size_t)acc_floats * sizeof(double), st));
   DevOut out;
   memset(&out, 0, sizeof(out));
-  out.work_counter = ctr + 4;
+  out.work_counter = reinterpret_cast<unsigned*>(ctr + 4);
   out.counters = ctr;
   out.target = target_dev;
   out.acc_stride = acc_floats;
@@ -961,7 +905,7 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
   IPT_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
   DevOut out;
   memset(&out, 0, sizeof(out));
-  out.work_counter = ctr + 4;
+  out.work_counter = reinterpret_cast<unsigned*>(ctr + 4);
   out.counters = ctr;
   out.target = target_dev;
   out.dldpx = (const float*)h->dldpx.ptr;

@@ -3,11 +3,13 @@
 // HBM layout.  All arrays are float4-vectorised so one triangle test is
 // four 16-byte loads and the whole small scene can be staged into shared memory with float4 copies.
 //   geom  [4*nT] : {n.xyz, k=dot(c,n)} {e0.xyz,e0.d} {e1.xyz,e1.d} {e2.xyz,e2.d}     64 B / triangle (BVH leaves)
-//   plane groups (brute-force mode): triangles whose (n, k) are bit-identical share one plane test
-//     planes [G]    : {n.xyz, k}                 16 B / group
-//     grange [G]    : {first slot, end slot}      8 B / group
-//     slot_edges [5*nSlots] : {out.xyz, d} x 5   80 B / quad slot: shared diagonal, 2 edges of a, 2 edges of b
-//     slot_tri [nSlots] : triangle ids (a, b)      8 B / slot
+//   stream [nStream] : the brute-force set as ONE record stream, walked with a single running address:
+//     per plane group (triangles whose (n, k) are value-equal share one plane test)
+//       {n.xyz, k}                                 the plane
+//       {bytes to the next group (int bits), -, -, -}
+//       per quad slot (two coplanar triangles sharing an exactly negated edge plane; five edge planes instead of six)
+//         {out.xyz, d} x 5                         shared diagonal, 2 edges of a, 2 edges of b
+//         {id a, id b (int bits; b = -1 unpaired), -, -}
 //   mat   [8*nT] : {Kd.rgb, Ns} {Ke.rgb, flags(bits)} {Kd/pi .rgb, 0} {n.xyz, 0} {Ks.rgb, area}
 //                  {R row0, 0} {R row1, 0} {R row2, 0}   (R = FromTwoVectors(z, n), path_trace.cu:102)   128 B / triangle
 //   light [3*nE] : {v0.xyz, cdf} {v1.xyz, p_t} {v2.xyz, tri index(bits)}             48 B / emissive
@@ -29,12 +31,9 @@ constexpr int kMatStride = 8;   // float4 records per triangle in `mat`
 
 struct DevScene {
   const float4* geom;          // [4 nT] plane + 3 edge planes per triangle; in BVH scenes stored in leaf order (slot j = triangle bvh_prims[j])
-  const float4* planes;
-  const int2* grange;
-  const float4* slot_edges;
-  const int2* slot_tri;     // triangle ids (a, b) of each quad slot; b = -1 for an unpaired triangle
+  const float4* stream;     // record stream of the brute-force set (see above)
   int nGroups;
-  int nSlots;             // quad slots (five edge records each)
+  int nStream;              // float4 records in `stream`
   const float4* mat;
   const float4* light;
   const float4* vtx;
@@ -44,7 +43,7 @@ struct DevScene {
   int bvh_depth;             // levels of the tree = entries of the per-thread traversal stack (<= 64)
   const int* bvh_prims;      // triangle index per BVH slot
   int nT, nE, nNodes;
-  int nBig;                  // BVH scenes: triangles kept out of the tree and tested brute force (planes / slot_* describe them)
+  int nBig;                  // BVH scenes: triangles kept out of the tree and tested brute force (`stream` describes them)
   int use_bvh;
   int plain;                 // no per-vertex normals and no specular lobe anywhere in the scene
   float cam[16];
@@ -68,7 +67,7 @@ struct DevRender {
 
 // counters[0..2] = paths, extension rays, shadow rays
 struct DevOut {
-  unsigned long long* work_counter;
+  unsigned* work_counter;       // next unclaimed work item (zeroed before the launch)
   unsigned long long* counters;
   float* partial;            // [n_pix * groups * 3]  forward
   const unsigned char* target;   // full-image RGB8 target (graph / grad)

@@ -93,13 +93,19 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   }
   __syncthreads();
 
+  // material / light records: shared memory at explicit 32-bit addresses in brute-force mode (intersect.cuh, lds4), global in BVH mode
+  const uint32_t smat_a = smem_addr(smat), slight_a = smem_addr(slight_s);
+  const uint32_t nT16 = (uint32_t)nT << 4;
+  auto M = [&](int field, int tri) -> float4 { return BVH ? mat[field * nT + tri] : lds4(smat_a + (uint32_t)field * nT16 + ((uint32_t)tri << 4)); };
+  auto LREC = [&](int li, int k) -> float4 { return BVH ? slight[3 * li + k] : lds4(slight_a + (uint32_t)(3 * li + k) * 16u); };
+
   const unsigned lane = threadIdx.x & 31u;
-  const long long n_items = (long long)rp.n_pix * rp.groups;
+  const unsigned n_items = (unsigned)rp.n_pix * (unsigned)rp.groups;   // < 2^31 (make_plan): 32-bit item arithmetic
   const f3 zero3 = mk3(0.0f, 0.0f, 0.0f);
 
   // ---- work item bookkeeping -------------------------------------------------------------------
   bool have_item = false, exhausted = false;
-  long long item = 0;
+  unsigned item = 0;
   int pixel = 0;
   float pix_c = 0.0f, pix_r = 0.0f;   // column / row of the item's pixel, as floats (one integer division per item)
   int s_next = 0, s_end = 0;      // next sample of the item to start / one past its last sample
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   // L_e of the path in flight: the emission record of its first hit (zero before that and for non-emitters)
   auto load_le = [&](float& e0, float& e1, float& e2) {
     e0 = e1 = e2 = 0.0f;
-    if (e_tri >= 0) { const float4 ke = mat[1 * nT + e_tri]; e0 = ke.x; e1 = ke.y; e2 = ke.z; }
+    if (e_tri >= 0) { const float4 ke = M(1, e_tri); e0 = ke.x; e1 = ke.y; e2 = ke.z; }
   };
 
   // one vertex of a pending adjoint sweep: Pbar_k = C_k + Kd_k b_k Pbar_{k+1}.
@@ -162,11 +168,11 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     v.a = vs[k * 64]; v.p = vs[k * 64 + 1];
     const int vtri = adj_tri(v);
     if (vtri >= 0) {
-      const float4 kd = mat[vtri];
+      const float4 kd = M(0, vtri);
       const int vlight = adj_light(v);
       const float vb = v.a.y, vg = v.a.w;
       float k0 = 0.0f, k1 = 0.0f, k2 = 0.0f;   // Ke_light * g
-      if (vlight >= 0) { const float4 lke = mat[1 * nT + vlight]; k0 = lke.x * vg; k1 = lke.y * vg; k2 = lke.z * vg; }
+      if (vlight >= 0) { const float4 lke = M(1, vlight); k0 = lke.x * vg; k1 = lke.y * vg; k2 = lke.z * vg; }
       const float g0 = v.p.x * fmaf(vb, pb0, k0), g1 = v.p.y * fmaf(vb, pb1, k1), g2 = v.p.z * fmaf(vb, pb2, k2);
       if (out.acc_in_smem == 2) { float* ga = out.block_acc + (size_t)blockIdx.x * out.acc_stride + 3 * vtri; atomicAdd(ga + 0, sw0 * g0); atomicAdd(ga + 1, sw1 * g1); atomicAdd(ga + 2, sw2 * g2); }
       else if (out.acc_in_smem) { float* ga = sacc + 3 * vtri; atomicAdd(ga + 0, sw0 * g0); atomicAdd(ga + 1, sw1 * g1); atomicAdd(ga + 2, sw2 * g2); }
@@ -180,8 +186,8 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         u.a = vs[(k - 1) * 64];
         const int utri = adj_tri(u), ulight = adj_light(u);
         if (utri >= 0 && ulight >= 0) {
-          const float4 lke = mat[1 * nT + ulight];
-          const float4 kd = mat[utri];
+          const float4 lke = M(1, ulight);
+          const float4 kd = M(0, utri);
           const float ug = u.a.w;
           const float k0 = lke.x * ug, k1 = lke.y * ug, k2 = lke.z * ug;
           if (out.acc_in_smem == 2) { float* ga = out.block_acc + (size_t)blockIdx.x * out.acc_stride + 3 * utri; atomicAdd(ga + 0, sw0 * (v.p.x * k0)); atomicAdd(ga + 1, sw1 * (v.p.y * k1)); atomicAdd(ga + 2, sw2 * (v.p.z * k2)); }
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     fin_left--;
     if (fin_left == 0) {
       if (MODE == MODE_RENDER) {
-        float* dst = out.partial + item * 3;
+        float* dst = out.partial + (size_t)item * 3;
         dst[0] = part0; dst[1] = part1; dst[2] = part2;
       }
       have_item = false;
@@ -224,6 +230,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     // (one radiance() call, path_trace.cu:111-144 / inv_path_trace.cu:109-150; the contribution
     //  prevMultiplier * (L_e + L_d) is applied in [D] once this bounce's shadow ray is resolved)
     bool ext_valid = false, sh_valid = false, end_after = false;
+    sh_dir = zero3;   // a ray slot that carries no ray has d = 0 (denom = 0 fails every plane's MIN_DOT test)
     if (active) {
       if (h.tri < 0) {
         // miss (path_trace.cu:116): the stale L_e / L_d are re-added with the new multiplier
@@ -235,9 +242,9 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         finalize();
       } else {
         const int tri = h.tri;
-        const float4 ma = mat[tri], mb = mat[1 * nT + tri];
+        const float4 ma = M(0, tri), mb = M(1, tri);
         const int flags = PLAIN ? (__float_as_int(mb.w) & TRI_NEG_Z) : __float_as_int(mb.w);
-        const f3 face_n = xyz(mat[3 * nT + tri]);
+        const f3 face_n = xyz(M(3, tri));
         const f3 hit = mk3(fmaf(rdir.x, h.t, rpos.x), fmaf(rdir.y, h.t, rpos.y), fmaf(rdir.z, h.t, rpos.z));
         const f3 ns = PLAIN ? face_n : shading_normal(sc, tri, flags, face_n, hit);
         if (MODE != MODE_GRAPH && bounce == 0) e_tri = tri;
@@ -270,8 +277,14 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         //      point; the shadow ray itself goes into this trip's dual intersection
         if (nE > 0) {
           const float u_pick = u16(rn.x >> 16), r1 = u16(rn.y >> 16), r2 = u16(rn.y & 0xffffu);
-          const int li = pick_light(slight, nE, u_pick);
-          const float4 la = slight[3 * li], lb = slight[3 * li + 1], lc = slight[3 * li + 2];
+          int li = 0;
+          if (BVH) {
+            li = pick_light(slight, nE, u_pick);
+          } else {
+            // pick_light's linear scan (path_trace.cu:39-51) over the shared-memory table (brute-force scenes have <= 128 lights)
+            while (li < nE - 1 && !(lds1f(slight_a + (uint32_t)(3 * li) * 16u + 12u) >= u_pick)) li++;
+          }
+          const float4 la = LREC(li, 0), lb = LREC(li, 1), lc = LREC(li, 2);
           const float sq = IPT_SQRT_UNIT(r1);   // r1 in [2^-17, 1)
           const float c1 = 1.0f - sq, c2 = sq * (1.0f - r2), c3 = r2 * sq;
           const f3 ep = mk3(fmaf(c3, lc.x, fmaf(c2, lb.x, c1 * la.x)), fmaf(c3, lc.y, fmaf(c2, lb.y, c1 * la.y)), fmaf(c3, lc.z, fmaf(c2, lb.z, c1 * la.z)));
@@ -279,13 +292,14 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
           const float cos_theta = dot3(ns, toLight);
           // written unconditionally (plain register definitions, no predicated copies); only read when sh_valid
           sh_valid = !(cos_theta < 0.0f);
-          sh_org = hit; sh_dir = toLight;
+          sh_org = hit;
+          if (sh_valid) sh_dir = toLight;
           sh_light = __float_as_int(lc.w); sh_tri = tri;
           sh_cos = cos_theta; sh_pt = lb.w; sh_gw = gweight;
           if (MODE != MODE_GRAPH && !PLAIN) {   // (plain scenes: BSDF(isDirect) is Kd of sh_tri, re-read in [D])
             f0 = ma.x; f1 = ma.y; f2 = ma.z;   // BSDF(isDirect = true): Kd, no 1/pi (path_trace.cu:14-17)
             if (sh_valid && (flags & TRI_ANY_KS)) {
-              const float4 mc = mat[4 * nT + tri];
+              const float4 mc = M(4, tri);
               const float co = phong_coeff(ns, rdir, toLight, ma.w);
               f0 = fmaf(mc.x, co, f0); f1 = fmaf(mc.y, co, f1); f2 = fmaf(mc.z, co, f2);
             }
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
             if (flags & TRI_NEG_Z) {
               nd = -hemi;
             } else {
-              const float4 r0 = mat[5 * nT + tri], r1 = mat[6 * nT + tri], r2 = mat[7 * nT + tri];
+              const float4 r0 = M(5, tri), r1 = M(6, tri), r2 = M(7, tri);
               nd = mk3(dot3(r0.x, r0.y, r0.z, hemi), dot3(r1.x, r1.y, r1.z, hemi), dot3(r2.x, r2.y, r2.z, hemi));
             }
             nd = IPT_NORMALIZE(nd);
@@ -321,11 +335,11 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
             gweight = gweight * gscale;
             gdst = tri;
           } else {
-            const float4 mp = mat[2 * nT + tri];   // Kd / pi, divided once at load (same IEEE division)
+            const float4 mp = M(2, tri);   // Kd / pi, divided once at load (same IEEE division)
             float i0 = mp.x, i1 = mp.y, i2 = mp.z;         // BSDF(isDirect = false)
             float coeff = cosn * rp.c_diff;                // canon v2: (1/(1/pi))/p_rr folded on the host
             if (!PLAIN && (flags & TRI_ANY_KS)) {
-              const float4 mc = mat[4 * nT + tri];
+              const float4 mc = M(4, tri);
               const float co = phong_coeff(ns, rdir, nd, ma.w);
               i0 = fmaf(mc.x, co, i0); i1 = fmaf(mc.y, co, i1); i2 = fmaf(mc.z, co, i2);
               if (flags & TRI_SPECULAR) coeff = (cosn / p_sample) / rp.p_rr;
@@ -367,18 +381,17 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       const unsigned need_mask = __ballot_sync(kFull, need);
       if (need_mask) {
         const int leader = __ffs(need_mask) - 1;
-        unsigned long long base = 0;
-        if ((int)lane == leader) base = atomicAdd(out.work_counter, (unsigned long long)__popc(need_mask));
+        unsigned base = 0;
+        if ((int)lane == leader) base = atomicAdd(out.work_counter, (unsigned)__popc(need_mask));   // overshoot <= one claim per lane: no wrap
         base = __shfl_sync(kFull, base, leader);
         if (need) {
-          const long long my = (long long)base + __popc(need_mask & ((1u << lane) - 1u));
+          const unsigned my = base + __popc(need_mask & ((1u << lane) - 1u));
           if (my < n_items) {
             have_item = true;
             item = my;
             // floor(my / groups) and floor(pixel / width) by multiplication with ceil(2^64 / d) (exact below 2^32)
-            const int pix_local = rp.groups == 1 ? (int)my
-                                  : (my < 0x100000000ll ? (int)__umul64hi((unsigned long long)my, rp.magic_groups) : (int)(my / rp.groups));
-            const int g = (int)(my - (long long)pix_local * rp.groups);
+            const int pix_local = rp.groups == 1 ? (int)my : (int)__umul64hi((unsigned long long)my, rp.magic_groups);
+            const int g = (int)(my - (unsigned)pix_local * (unsigned)rp.groups);
             {
               const int lr = rp.width == 1 ? pix_local : (int)__umul64hi((unsigned long long)pix_local, rp.magic_width);
               const int c = pix_local - lr * rp.width;
@@ -425,15 +438,16 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       n_paths++;
     }
     if (__all_sync(kFull, !ext_valid && !sh_valid && !have_item && exhausted)) break;
+    if (!ext_valid) rdir = zero3;   // (kept in the state itself: a select at the call is re-evaluated inside the group loop)
 
     // =========== [C] closest hits: extension ray and shadow ray ==========================================
     HitRec hs;
     if (!BVH) {
-      closest_hit_small2(ss, rpos, ext_valid ? rdir : zero3, sh_org, sh_valid ? sh_dir : zero3, h, hs);
+      closest_hit_small2(ss, rpos, rdir, sh_org, sh_dir, h, hs);
     } else {
       h.t = INFINITY; h.tri = -1;
       hs.t = INFINITY; hs.tri = -1;
-      if (ss.nGroups > 0) closest_hit_small2(ss, rpos, ext_valid ? rdir : zero3, sh_org, sh_valid ? sh_dir : zero3, h, hs);
+      if (ss.nGroups > 0) closest_hit_small2(ss, rpos, rdir, sh_org, sh_dir, h, hs);
       if (ext_valid) h = closest_hit_bvh(sc, rpos, rdir, bvh_stack, h);
       if (sh_valid) hs = closest_hit_bvh(sc, sh_org, sh_dir, bvh_stack, hs);
     }
@@ -444,9 +458,9 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     if (sh_valid) {
       d0 = d1 = d2 = 0.0f;
       if (hs.tri >= 0) {
-        const float4 lmb = mat[1 * nT + sh_light];
+        const float4 lmb = M(1, sh_light);
         const f3 shit = mk3(fmaf(sh_dir.x, hs.t, sh_org.x), fmaf(sh_dir.y, hs.t, sh_org.y), fmaf(sh_dir.z, hs.t, sh_org.z));
-        const f3 ln = PLAIN ? xyz(mat[3 * nT + sh_light]) : shading_normal(sc, sh_light, __float_as_int(lmb.w), xyz(mat[3 * nT + sh_light]), shit);
+        const f3 ln = PLAIN ? xyz(M(3, sh_light)) : shading_normal(sc, sh_light, __float_as_int(lmb.w), xyz(M(3, sh_light)), shit);
         const float cos_tp = -dot3(ln, sh_dir);
         if (!(cos_tp < 0.0f) && hs.tri == sh_light) {
           if (MODE == MODE_GRAPH) {
@@ -470,7 +484,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
             }
           } else {
             const float g = (sh_cos * cos_tp) / ((hs.t * hs.t) * sh_pt);
-            if (PLAIN) { const float4 kd = mat[sh_tri]; f0 = kd.x; f1 = kd.y; f2 = kd.z; }   // BSDF(isDirect = true) = Kd (path_trace.cu:14-17)
+            if (PLAIN) { const float4 kd = M(0, sh_tri); f0 = kd.x; f1 = kd.y; f2 = kd.z; }   // BSDF(isDirect = true) = Kd (path_trace.cu:14-17)
             d0 = f0 * (lmb.x * g); d1 = f1 * (lmb.y * g); d2 = f2 * (lmb.z * g);
             if (MODE == MODE_GRAD) {
               const int k = path_len - 1;   // the vertex recorded in [A] of this trip
@@ -654,8 +668,8 @@ __global__ void k_set_kd(float4* __restrict__ mat, const float* __restrict__ kd,
 size_t paths_smem_bytes(const DevScene& sc, int acc_floats) {
   size_t b = (size_t)acc_floats * sizeof(float);
   if (!sc.use_bvh || sc.nE <= kLightSmemMax) b += (size_t)3 * sc.nE * sizeof(float4);
-  if (!sc.use_bvh) b += small_scene_smem_bytes(sc.nSlots, sc.nGroups) + (size_t)kMatStride * sc.nT * sizeof(float4);
-  else b += bvh_stack_bytes(sc) + (sc.nGroups > 0 ? small_scene_smem_bytes(sc.nSlots, sc.nGroups) : 0);
+  if (!sc.use_bvh) b += small_scene_smem_bytes(sc.nStream) + (size_t)kMatStride * sc.nT * sizeof(float4);
+  else b += bvh_stack_bytes(sc) + (sc.nGroups > 0 ? small_scene_smem_bytes(sc.nStream) : 0);
   return b;
 }
 

@@ -1,0 +1,103 @@
+// scene_handle.h -- the scene handle behind the C ABI and the helpers api.cu shares with inverse.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+
+#include "../../include/ipt_b200.h"
+#include "device_scene.h"
+#include "kernels.h"
+#include "scene_host.h"
+
+namespace ipt {
+
+int fail(const std::string& msg);   // sets the thread's last error, returns -1
+extern std::atomic<unsigned long long> g_launches;
+
+#define IPT_CUDA(call)                                                                                        \
+  do {                                                                                                        \
+    cudaError_t e__ = (call);                                                                                 \
+    if (e__ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e__));                 \
+  } while (0)
+
+struct Scratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, need);
+    if (e == cudaSuccess) bytes = need;
+    return e;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+};
+
+struct SceneHandle {
+  HostScene host;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  float4* geom = nullptr;
+  float4* bf_stream = nullptr;   // record stream of the brute-force set (device_scene.h)
+  int n_groups = 0;
+  int n_stream = 0;
+  float4* mat = nullptr;
+  float4* light = nullptr;
+  float4* vtx = nullptr;
+  float4* bvh_nodes = nullptr;
+  float4* bvh_wide = nullptr;
+  int bvh_root_desc = 0;
+  int bvh_depth = 1;
+  int* bvh_prims = nullptr;
+  int n_nodes = 0;
+  int n_big = 0;
+  bool use_bvh = false;
+  bool host_only = false;
+  // knobs copied from the loading thread's settings (iptSetTraversalMode / iptSetBvhLargeTriangleLimit / iptSetIntegrator)
+  int traversal_mode = 0, big_max = 128, integrator = 0, wf_slots = 1 << 24;
+  // ring of CUDA event pairs bracketing the last kEventRing k_paths launches (roofline timing without
+  // synchronising inside a timed loop)
+  static constexpr int kEventRing = 64;
+  cudaEvent_t ev_start[kEventRing] = {}, ev_stop[kEventRing] = {};
+  unsigned long long ev_count = 0;   // loaded with iptSetDevice(-2): tables only, no device arrays
+  int* host_live = nullptr;          // pinned word for the wavefront integrator's live count
+  Scratch wavefront;
+  Scratch partial, counters, cnt_out, trace_counter, block_acc, vstacks, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
+  std::mutex mutex;
+
+  DevScene dev() const {
+    DevScene d;
+    d.geom = geom; d.stream = bf_stream; d.nGroups = n_groups; d.nStream = n_stream; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
+    d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.nBig = n_big; d.use_bvh = use_bvh ? 1 : 0; d.plain = (!host.any_vn && !host.any_specular) ? 1 : 0;
+    memcpy(d.cam, host.cam, sizeof(d.cam));
+    return d;
+  }
+  void destroy() {
+    if (host_only) return;
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(geom); cudaFree(bf_stream); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_wide); cudaFree(bvh_prims);
+    Scratch* all[] = {&wavefront, &partial, &counters, &cnt_out, &trace_counter, &block_acc, &vstacks, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
+    for (Scratch* s : all) s->release();
+    if (host_live) cudaFreeHost(host_live);
+    if (stream) cudaStreamDestroy(stream);
+    for (int i = 0; i < kEventRing; i++) { if (ev_start[i]) cudaEventDestroy(ev_start[i]); if (ev_stop[i]) cudaEventDestroy(ev_stop[i]); }
+  }
+};
+
+SceneHandle* checked(void* p);          // registry lookup; null + error for a stale / foreign pointer
+SceneHandle* checked_device(void* p);   // ... and the scene must live on a GPU
+
+struct Plan {
+  DevRender rp;
+  int rows;
+};
+int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan);
+int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev, cudaStream_t st);
+
+}  // namespace ipt

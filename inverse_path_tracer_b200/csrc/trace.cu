@@ -162,7 +162,7 @@ static size_t trace_bvh_smem_bytes(const DevScene& sc) { return bvh_stack_bytes(
 // brute-force pass over the scene's shared-memory set (whole small scene / large-triangle set of a BVH scene)
 static cudaError_t launch_trace_small(const DevScene& sc, const float* rays, int n_direct, const int* n_live, int cap, int* tri, float* t, int sm_count,
                                       cudaStream_t st) {
-  const size_t smem = small_scene_smem_bytes(sc.nSlots, sc.nGroups);
+  const size_t smem = small_scene_smem_bytes(sc.nStream);
   cudaError_t e = cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long want = n_live ? (long long)sm_count * 16 : ((long long)n_direct + kBlock - 1) / kBlock;
@@ -181,6 +181,7 @@ cudaError_t launch_trace_bounce(const DevScene& sc, const float* rays, const int
     if (e != cudaSuccess) return e;
     *n_launches += 1;
   }
+  if (!sc.use_bvh) return cudaSuccess;   // brute-force scene driven through the wavefront (iptSceneSetIntegrator(2): A/B only)
   const size_t smem = trace_bvh_smem_bytes(sc);
   e = cudaFuncSetAttribute(k_trace_rays_bvh<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -32,7 +32,7 @@ EXPORTS = ["loadScene", "freeScene", "createImage", "createGraph", "getMaterials
            "iptRender", "iptRenderDevice", "iptCreateImageEx", "iptCreateGraphEx", "iptGraphAccumulateDevice",
            "iptGraphCompress", "iptRenderGrad", "iptRenderGradDevice", "iptSetMaterialsDevice", "iptBuildBVH",
            "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder", "iptTraceRaysStatsDevice",
-           "iptSetIntegrator", "iptMeasureCopyGBps",
+           "iptSetIntegrator", "iptSceneSetIntegrator", "iptMeasureCopyGBps",
            "iptSetBvhLargeTriangleLimit", "iptSceneLargeTriangles", "iptGraphCompressDevice"]
 
 
@@ -121,8 +121,9 @@ def set_bvh_large_triangle_limit(max_count=128):
 
 
 def set_integrator(mode=0, wavefront_slots=0):
-    """Forward integrator for BVH scenes: 0 auto (wavefront), 1 persistent megakernel, 2 wavefront;
-    wavefront_slots bounds the paths in flight per batch (0 = default)."""
+    """Forward integrator of BVH scenes LOADED AFTERWARDS from this thread: 0 auto (wavefront), 1 persistent
+    megakernel, 2 wavefront; wavefront_slots bounds the paths in flight per batch (0 = default).
+    Scene.set_integrator changes one loaded scene."""
     if lib().iptSetIntegrator(int(mode), int(wavefront_slots)) != 0:
         raise ValueError(last_error())
 
@@ -183,6 +184,12 @@ class Scene:
     def from_file(cls, scenefile, asset_root=None, **kw):
         from .ipt_cuda import parse_scene_file
         return cls(parse_scene_file(scenefile), asset_root=asset_root, **kw)
+
+    def set_integrator(self, mode=0, wavefront_slots=0):
+        """forward integrator of this (BVH) scene: 0 auto (wavefront), 1 persistent megakernel, 2 wavefront"""
+        L = lib()
+        L.iptSceneSetIntegrator.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        _check(L.iptSceneSetIntegrator(self.h, int(mode), int(wavefront_slots)), "iptSceneSetIntegrator")
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:

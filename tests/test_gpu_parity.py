@@ -125,19 +125,30 @@ def test_wavefront_integrator_bit_exact(ipt, oracle, scene, w, h, spp, depth, gs
     pg = ipt.default_params(width=w, height=h, spp=spp, max_depth=depth, seed=77, group_samples=gs)
     po = oracle.make_params(w, h, spp, max_depth=depth, seed=77, group_samples=gs)
     img_o, cnt_o = o.render(po)
-    try:
-        ipt.set_integrator(2, slots)
-        img_w, cnt_w = g.render(pg)
-        shard = ipt.default_params(width=w, height=h, spp=spp, max_depth=depth, seed=77, group_samples=gs, row_begin=1, row_end=h, row_step=3)
-        img_s, _ = g.render(shard)
-        ipt.set_integrator(1, 0)
-        img_m, cnt_m = g.render(pg)
-    finally:
-        ipt.set_integrator(0, 0)
+    g.set_integrator(2, slots)
+    img_w, cnt_w = g.render(pg)
+    shard = ipt.default_params(width=w, height=h, spp=spp, max_depth=depth, seed=77, group_samples=gs, row_begin=1, row_end=h, row_step=3)
+    img_s, _ = g.render(shard)
+    g.set_integrator(1, 0)
+    img_m, cnt_m = g.render(pg)
     assert cnt_w == cnt_o and cnt_m == cnt_o
     assert img_w.tobytes() == img_o.tobytes(), "wavefront vs oracle: max abs diff %g" % np.abs(img_w - img_o).max()
     assert img_m.tobytes() == img_o.tobytes()
     assert img_s.tobytes() == img_o[1::3].tobytes()
+
+
+def test_wavefront_on_bruteforce_scene_equals_oracle(ipt, oracle):
+    """the wavefront integrator can also drive a brute-force (shared-memory) scene -- Scene.set_integrator(2), used for
+    the wavefront-vs-megakernel A/B on the Cornell box (profiles/r02_cornell_wavefront_ab.txt); same image, bit for bit"""
+    objects = _scene0(oracle)
+    g = ipt.Scene(objects, asset_root=ASSETS)
+    o = oracle.OracleScene(objects, ASSETS)
+    assert not g.uses_bvh
+    img_o, cnt_o = o.render(oracle.make_params(48, 40, 8, max_depth=6, seed=9))
+    for integ in (2, 0):
+        g.set_integrator(integ, 0)
+        img_g, cnt_g = g.render(ipt.default_params(width=48, height=40, spp=8, max_depth=6, seed=9))
+        assert cnt_g == cnt_o and img_g.tobytes() == img_o.tobytes(), integ
 
 
 def test_large_triangle_set_does_not_change_results(ipt, oracle):
@@ -159,13 +170,12 @@ def test_large_triangle_set_does_not_change_results(ipt, oracle):
             tri_g, t_g = g.trace(rays)
             assert np.array_equal(tri_g, tri_o) and t_g.tobytes() == t_o.tobytes(), "limit %d" % limit
             for integ in (1, 2):
-                ipt.set_integrator(integ, 0)
+                g.set_integrator(integ, 0)
                 img_g, cnt_g = g.render(ipt.default_params(width=40, height=32, spp=6, max_depth=5, seed=4))
                 assert cnt_g == cnt_o and img_g.tobytes() == img_o.tobytes(), "limit %d integrator %d" % (limit, integ)
             g.close()
     finally:
         ipt.set_bvh_large_triangle_limit(128)
-        ipt.set_integrator(0, 0)
     assert sizes == [18, 7, 0]
 
 
@@ -181,14 +191,11 @@ def test_emissive_mesh_many_lights(ipt, oracle, tmp_path):
     assert g.uses_bvh and g.nE == o.nE == 1282
     po = oracle.make_params(40, 32, 6, max_depth=5, seed=21)
     img_o, cnt_o = o.render(po)
-    try:
-        for integ in (1, 2):
-            ipt.set_integrator(integ, 0)
-            img_g, cnt_g = g.render(ipt.default_params(width=40, height=32, spp=6, max_depth=5, seed=21))
-            assert cnt_g == cnt_o, integ
-            assert img_g.tobytes() == img_o.tobytes(), "integrator %d: max abs diff %g" % (integ, np.abs(img_g - img_o).max())
-    finally:
-        ipt.set_integrator(0, 0)
+    for integ in (1, 2):
+        g.set_integrator(integ, 0)
+        img_g, cnt_g = g.render(ipt.default_params(width=40, height=32, spp=6, max_depth=5, seed=21))
+        assert cnt_g == cnt_o, integ
+        assert img_g.tobytes() == img_o.tobytes(), "integrator %d: max abs diff %g" % (integ, np.abs(img_g - img_o).max())
     # the adjoint (megakernel, lights in global memory) against the oracle's
     target = np.random.RandomState(2).randint(0, 256, (32, 40, 3)).astype(np.uint8)
     loss_g, grad_g, _ = g.render_grad(ipt.default_params(width=40, height=32, spp=6, max_depth=5, seed=21), target)
@@ -489,24 +496,21 @@ def test_fuzz_scenes_bit_exact_all_integrators(ipt, oracle, chunk):
     rng = np.random.RandomState(7 + chunk)
     rays = np.concatenate([rng.uniform(-2, 2, (3000, 3)) + [0, 0, 4], rng.normal(size=(3000, 3))], 1).astype(np.float32)
     rays[:, 3:] /= np.linalg.norm(rays[:, 3:], axis=1, keepdims=True)
-    try:
-        for case in cases:
-            objs = [{"pos": [0, 0, 5], "ori": [0.1, 0.2, 0.3], "scl": [1, 1, 1], "obj": "./fuzz/%s.obj" % case, "mtl": "./fuzz/%s.mtl" % case}] + cornell
-            o = oracle.OracleScene(objs, ASSETS)
-            img_o, cnt_o = o.render(oracle.make_params(32, 24, 4, max_depth=5, seed=3))
-            tri_o, t_o = o.trace(rays)
-            for mode in (0, 2):
-                g = ipt.Scene(objs, asset_root=ASSETS, traversal_mode=mode)
-                tri_g, t_g = g.trace(rays)
-                assert np.array_equal(tri_g, tri_o) and t_g.tobytes() == t_o.tobytes(), (case, mode)
-                for integ in ((1,) if mode == 0 else (1, 2)):
-                    ipt.set_integrator(integ, 0)
-                    img_g, cnt_g = g.render(ipt.default_params(width=32, height=24, spp=4, max_depth=5, seed=3))
-                    assert cnt_g == cnt_o, (case, mode, integ)
-                    assert img_g.tobytes() == img_o.tobytes(), (case, mode, integ, float(np.nanmax(np.abs(img_g - img_o))))
-                g.close()
-    finally:
-        ipt.set_integrator(0, 0)
+    for case in cases:
+        objs = [{"pos": [0, 0, 5], "ori": [0.1, 0.2, 0.3], "scl": [1, 1, 1], "obj": "./fuzz/%s.obj" % case, "mtl": "./fuzz/%s.mtl" % case}] + cornell
+        o = oracle.OracleScene(objs, ASSETS)
+        img_o, cnt_o = o.render(oracle.make_params(32, 24, 4, max_depth=5, seed=3))
+        tri_o, t_o = o.trace(rays)
+        for mode in (0, 2):
+            g = ipt.Scene(objs, asset_root=ASSETS, traversal_mode=mode)
+            tri_g, t_g = g.trace(rays)
+            assert np.array_equal(tri_g, tri_o) and t_g.tobytes() == t_o.tobytes(), (case, mode)
+            for integ in ((1,) if mode == 0 else (1, 2)):
+                g.set_integrator(integ, 0)
+                img_g, cnt_g = g.render(ipt.default_params(width=32, height=24, spp=4, max_depth=5, seed=3))
+                assert cnt_g == cnt_o, (case, mode, integ)
+                assert img_g.tobytes() == img_o.tobytes(), (case, mode, integ, float(np.nanmax(np.abs(img_g - img_o))))
+            g.close()
 
 
 def test_graph_data_device_compress_equals_host(ipt, oracle):

@@ -31,9 +31,9 @@ if a.scene == "cornell":
     objs = [{"pos": [0, 0, 4], "ori": [0, 0, 0], "scl": [2, 2, 2], "obj": "./CornellBox/CornellBox-Empty-CO.obj", "mtl": "./CornellBox/CornellBox-Empty-CO.mtl"}]
 else:
     objs = parse_scene_file(os.path.join(ASSETS, "scenes", "0.txt"))
-if a.integrator:
-    ipt.set_integrator(a.integrator)
 sc = ipt.Scene(objs, asset_root=ASSETS, traversal_mode=a.traversal)
+if a.integrator:
+    sc.set_integrator(a.integrator)
 rng = np.random.RandomState(0)
 target = rng.randint(0, 256, (a.size, a.size, 3)).astype(np.uint8)
 for i in range(a.reps):

@@ -117,7 +117,7 @@ def main():
     if a.only_render == 3:
         pass
     elif a.only_render:
-        ipt.set_integrator(a.only_render, 0)
+        sc.set_integrator(a.only_render, 0)
         for rep in range(a.reps):
             p = ipt.default_params(width=a.size, height=a.size, spp=a.spp, max_depth=a.depth, seed=rep)
             img, cnt = sc.render(p)
@@ -140,7 +140,7 @@ def bvh_and_render(a, sc, L):
             (boxes.nbytes + tab["center"].nbytes) / 1e6, time.time() - t0, ni.shape[0], int(np.ceil(np.log2(max(ni.shape[0], 2))))))
     images = {}
     for integ, name in ((1, "megakernel"), (2, "wavefront")):
-        ipt.set_integrator(integ, 0)
+        sc.set_integrator(integ, 0)
         for rep in range(a.reps):
             p = ipt.default_params(width=a.size, height=a.size, spp=a.spp, max_depth=a.depth, seed=rep)
             img, cnt = sc.render(p)
@@ -149,7 +149,7 @@ def bvh_and_render(a, sc, L):
             print("render [%s] %dx%dx%d depth %d: %s device %.1f ms -> %.1f Mrays/s, %.1f Mpaths/s, mean radiance %.4f" % (
                 name, a.size, a.size, a.spp, a.depth, cnt, ms, rays / ms / 1e3, cnt["paths"] / ms / 1e3, float(img.mean())))
             images[(integ, rep)] = img
-    ipt.set_integrator(0, 0)
+    sc.set_integrator(0, 0)
     for rep in range(a.reps):
         print("wavefront image == megakernel image (seed %d): %s" % (rep, images[(1, rep)].tobytes() == images[(2, rep)].tobytes()))
 
