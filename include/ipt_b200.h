@@ -87,6 +87,12 @@ int iptGetTriangleTable(void* scene, float* verts, float* kd, float* ks, float* 
                         float* normal, float* center, float* area);
 int iptGetCamera(void* scene, float* m16);
 
+/* Concurrency: a scene handle runs ONE call at a time.  Every entry point takes the handle's lock while it enqueues,
+ * and the device-pointer (`*Device`) calls, which run on a caller-chosen stream, are chained on the device as well: each
+ * waits for the scene's previous call (an event recorded after it) before it touches the handle's scratch buffers, so
+ * calls issued on different streams or threads serialise instead of sharing the work counter / partial sums.  Use one
+ * handle per stream (or per GPU) for concurrent work.  Inside a CUDA stream capture the chaining events are skipped. */
+
 /* closest hit for n rays (p.xyz, d.xyz); tri = -1 and t = +inf on a miss.  Host buffers. */
 int iptTraceRays(void* scene, const float* rays, int n, int* tri, float* t);
 /* same on device memory, asynchronous on `stream` (a cudaStream_t) */
@@ -155,6 +161,37 @@ int iptSceneLargeTriangles(void* scene);
  * the number of live paths back after every bounce (one stream synchronisation per bounce). */
 int iptSetIntegrator(int mode, int wavefront_slots);
 int iptSceneSetIntegrator(void* scene, int mode, int wavefront_slots);
+
+/* ---- part 3: the inverse loop inside the library (new; the reference's material recovery is the GCN of ipt.py) --------
+ * One optimiser object per (scene, GPU).  iptInverseStep enqueues whole iterations on the scene's own stream -- forward
+ * render of this rank's row shard at p->spp samples (seed = first_seed + i), loss against the target (the loss of
+ * iptRenderGrad), path adjoint, sum of [loss, dLoss/dKd] over the `world` ranks that share the image, Adam step
+ * (torch.optim.Adam's arithmetic, float32), clamp to [kd_min, kd_max], new albedos into the scene -- and returns without
+ * waiting.  With world > 1 the sum is part of the update kernel: every rank stores its partial sums into every peer's
+ * mailbox over NVLink and adds the `world` vectors in rank order, so all ranks hold bit-identical albedos without a
+ * broadcast.  The mailboxes are ordinary device allocations exchanged once: iptInverseMailbox returns the local
+ * pointer and/or a 64-byte CUDA IPC handle; iptInverseConnect takes either raw peer pointers (ranks in one process)
+ * or the `world` x 64 bytes of IPC handles gathered from all ranks (one process per GPU).  A peer that does not arrive
+ * within timeout_ms makes the next iptInverseState fail instead of hanging the GPU. */
+typedef struct IptInverseConfig {
+  float lr, beta1, beta2, eps;   /* Adam; defaults 0.02, 0.9, 0.999, 1e-8 */
+  float kd_min, kd_max;          /* clamp after every step; defaults 1e-3, 1 */
+  int rank, world;               /* this GPU's place among the GPUs sharing the image (row shard = p->row_begin/row_step) */
+  int timeout_ms;                /* exchange timeout; default 10000 */
+} IptInverseConfig;
+void iptInverseDefaultConfig(IptInverseConfig* cfg);
+/* target_dev: height*width*3 bytes on the scene's device, caller-owned, must outlive the optimiser.  Starts from the
+ * scene's current albedos. */
+int iptInverseCreate(void* scene, const IptRenderParams* p, const unsigned char* target_dev, const IptInverseConfig* cfg, void** opt);
+int iptInverseMailbox(void* opt, void** mailbox_dev, void* ipc_handle64);
+int iptInverseConnect(void* opt, void* const* peer_mailboxes, const void* ipc_handles);
+/* albedos (nT*3 floats, host) into the optimiser and the scene; reset_moments != 0 also clears Adam's state and step count */
+int iptInverseSetKd(void* opt, const float* kd_host, int reset_moments);
+int iptInverseStep(void* opt, unsigned long long first_seed, int n_steps);
+/* waits for the enqueued steps; loss = global loss of the last step, kd_host[nT*3], steps = iterations applied,
+ * loss_history[history_count] = the last losses, oldest first (any pointer may be NULL) */
+int iptInverseState(void* opt, double* loss, float* kd_host, unsigned long long* steps, double* loss_history, int history_count);
+int iptInverseDestroy(void* opt);
 
 int iptWritePNG(const char* path, const unsigned char* rgb, int width, int height);
 int iptReadPNG(const char* path, unsigned char* rgb, int capacity_bytes, int* width, int* height);

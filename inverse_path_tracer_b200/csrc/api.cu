@@ -371,7 +371,7 @@ int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan) {
 }
 
 int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev,
-                          cudaStream_t st) {
+                   cudaStream_t st, bool resolve) {
   const DevScene sc = h->dev();
   const DevRender& rp = plan.rp;
   IPT_CUDA(h->partial.reserve((size_t)rp.n_pix * rp.groups * 3 * sizeof(float)));
@@ -407,8 +407,60 @@ int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned ch
     h->ev_count++;
     g_launches += 1;
   }
+  if (!resolve) return 0;
   IPT_CUDA(launch_resolve(out.partial, rp.n_pix, rp.groups, img_dev, img8_dev, st));
   g_launches += 1;
+  return 0;
+}
+
+int launch_grad_pass(SceneHandle* h, const Plan& plan, const unsigned char* target_dev, double* lossgrad_dev, cudaStream_t st) {
+  const DevScene sc = h->dev();
+  const DevRender& rp = plan.rp;
+  const int nT = sc.nT;
+  if (nT == 0) return 0;
+  IPT_CUDA(h->counters.reserve(8 * sizeof(unsigned long long)));
+  unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
+  IPT_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
+  DevOut out;
+  memset(&out, 0, sizeof(out));
+  out.work_counter = reinterpret_cast<unsigned*>(ctr + 4);
+  out.counters = ctr;
+  out.target = target_dev;
+  out.dldpx = (const float*)h->dldpx.ptr;
+  out.acc_stride = 3 * nT;
+  // gradient tiles: one [3 nT] float tile per block in global memory, updated with fire-and-forget float
+  // reductions (shared-memory float atomics are compare-and-swap loops on this architecture); scenes whose
+  // tiles would be too large fall back to double atomics on the result itself
+  const char* acc_env = getenv("IPT_GRAD_ACC");   // developer A/B: 0 = global double, 1 = shared tile, 2 = global tile
+  size_t smem = paths_smem_bytes(sc, 0);
+  out.acc_in_smem = (3 * (size_t)nT <= 65536) ? 2 : 0;
+  if (acc_env && *acc_env) out.acc_in_smem = atoi(acc_env);
+  if (out.acc_in_smem == 1) smem = paths_smem_bytes(sc, 3 * nT);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, sc, smem);
+  if (out.acc_in_smem) {
+    IPT_CUDA(h->block_acc.reserve((size_t)grid * 3 * nT * sizeof(float)));
+    out.block_acc = (float*)h->block_acc.ptr;
+    if (out.acc_in_smem == 2) IPT_CUDA(cudaMemsetAsync(out.block_acc, 0, (size_t)grid * 3 * nT * sizeof(float), st));
+  } else {
+    out.global_acc = lossgrad_dev + 1;
+  }
+  // adjoint vertex stacks: two halves of max_depth 32-byte vertices per resident thread (no initialisation needed:
+  // a sweep only reads what its own path wrote)
+  out.vdepth = rp.max_depth;
+  IPT_CUDA(h->vstacks.reserve((size_t)grid * paths_block_threads() * 2 * (size_t)out.vdepth * 32));
+  out.vstacks = (float4*)h->vstacks.ptr;
+  {
+    const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
+    IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
+    IPT_CUDA(launch_paths(MODE_GRAD_ID, sc, rp, out, grid, smem, st));
+    IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
+    h->ev_count++;
+  }
+  g_launches += 1;
+  if (out.acc_in_smem) {
+    IPT_CUDA(launch_reduce_blocks(out.block_acc, grid, 3 * nT, lossgrad_dev + 1, 0, 0, st));
+    g_launches += 1;
+  }
   return 0;
 }
 
@@ -459,7 +511,7 @@ int iptSceneSetIntegrator(void* scene, int mode, int wavefront_slots) {
   if (!h) return -1;
   if (mode < 0 || mode > 2) return fail("integrator must be 0, 1 or 2");
   if (wavefront_slots < 0) return fail("wavefront_slots must be >= 0");
-  std::lock_guard<std::mutex> lk(h->mutex);
+  std::lock_guard<std::recursive_mutex> lk(h->mutex);
   h->integrator = mode;
   h->wf_slots = wavefront_slots > 0 ? wavefront_slots : (1 << 24);
   return 0;
@@ -536,6 +588,7 @@ int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mt
   cudaError_t e = cudaSetDevice(dev);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->busy, cudaEventDisableTiming);
   for (int i = 0; i < SceneHandle::kEventRing && e == cudaSuccess; i++) {
     e = cudaEventCreate(&h->ev_start[i]);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev_stop[i]);
@@ -570,10 +623,24 @@ void freeScene(void* scenePtr) {
   delete h;
 }
 
+// albedos changed on the device (iptSetMaterialsDevice, iptInverseStep) are read back before the host table is used, so
+// getMaterials always reflects the last set, like the reference's (inv_path_trace.cu:210-214)
+static void sync_host_kd(SceneHandle* h) {
+  if (!h->kd_dirty || h->host_only) return;
+  const size_t nT = h->host.tris.size();
+  std::vector<float4> kd(nT);
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (nT && cudaMemcpy(kd.data(), h->mat, nT * sizeof(float4), cudaMemcpyDeviceToHost) == cudaSuccess)
+    for (size_t i = 0; i < nT; i++) { h->host.tris[i].mat.kd[0] = kd[i].x; h->host.tris[i].mat.kd[1] = kd[i].y; h->host.tris[i].mat.kd[2] = kd[i].z; }
+  h->kd_dirty = false;
+}
+
 void getMaterials(void* scenePtr, float* materials) {
   SceneHandle* h = checked(scenePtr);
   if (!h || !materials) return;
-  std::lock_guard<std::mutex> lk(h->mutex);
+  std::lock_guard<std::recursive_mutex> lk(h->mutex);
+  sync_host_kd(h);
   for (size_t i = 0; i < h->host.tris.size(); i++)
     for (int j = 0; j < 3; j++) materials[3 * i + j] = h->host.tris[i].mat.kd[j];
 }
@@ -581,24 +648,29 @@ void getMaterials(void* scenePtr, float* materials) {
 void setMaterials(void* scenePtr, float* materials) {
   SceneHandle* h = checked(scenePtr);
   if (!h || !materials) return;
-  std::lock_guard<std::mutex> lk(h->mutex);
+  std::lock_guard<std::recursive_mutex> lk(h->mutex);
   for (size_t i = 0; i < h->host.tris.size(); i++)
     for (int j = 0; j < 3; j++) h->host.tris[i].mat.kd[j] = materials[3 * i + j];
   if (h->host_only) return;
   std::vector<float4> mat;
   pack_materials(h->host, &mat);
+  // the legacy call is fully synchronous like the reference's (scene.h:154-162 writes managed memory between renders):
+  // wait for everything queued on the device, on whatever stream, before the table is replaced
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();
   if (!mat.empty()) cudaMemcpy(h->mat, mat.data(), mat.size() * sizeof(float4), cudaMemcpyHostToDevice);
+  h->kd_dirty = false;
 }
 
 int iptSetMaterialsDevice(void* scene, const float* kd_dev, void* stream) {
   SceneHandle* h = checked_device(scene);
   if (!h || !kd_dev) return fail("iptSetMaterialsDevice: bad arguments");
   IPT_CUDA(cudaSetDevice(h->device));
+  CallGuard guard(h, (cudaStream_t)stream);
   const int nT = (int)h->host.tris.size();
   IPT_CUDA(launch_set_kd(h->mat, kd_dev, nT, (cudaStream_t)stream));
   g_launches += 1;
+  h->kd_dirty = true;   // getMaterials / the triangle table read the albedos back from the device
   return 0;
 }
 
@@ -617,6 +689,8 @@ int iptGetTriangleTable(void* scene, float* verts, float* kd, float* ks, float* 
                         float* center, float* area) {
   SceneHandle* h = checked(scene);
   if (!h) return -1;
+  std::lock_guard<std::recursive_mutex> lk(h->mutex);
+  sync_host_kd(h);
   for (size_t i = 0; i < h->host.tris.size(); i++) {
     const HostTriangle& t = h->host.tris[i];
     for (int j = 0; j < 3; j++) {
@@ -647,6 +721,7 @@ int iptTraceRaysDevice(void* scene, const float* rays_dev, int n, int* tri_dev, 
   if (n < 0 || (n > 0 && (!rays_dev || !tri_dev || !t_dev))) return fail("iptTraceRaysDevice: bad arguments");
   if (n == 0) return 0;
   IPT_CUDA(cudaSetDevice(h->device));
+  CallGuard guard(h, (cudaStream_t)stream);
   IPT_CUDA(h->trace_counter.reserve(sizeof(unsigned long long)));
   IPT_CUDA(launch_trace_rays(h->dev(), rays_dev, n, tri_dev, t_dev, (unsigned long long*)h->trace_counter.ptr, h->sm_count, (cudaStream_t)stream));
   g_launches += (h->use_bvh && h->n_big > 0) ? 2 : 1;
@@ -659,6 +734,7 @@ int iptTraceRaysStatsDevice(void* scene, const float* rays_dev, int n, int* tri_
   if (n <= 0 || !rays_dev || !tri_dev || !t_dev || !stats_dev) return fail("iptTraceRaysStatsDevice: bad arguments");
   if (!h->use_bvh) return fail("iptTraceRaysStatsDevice: the scene is in brute-force mode (no BVH to instrument)");
   IPT_CUDA(cudaSetDevice(h->device));
+  CallGuard guard(h, (cudaStream_t)stream);
   IPT_CUDA(cudaMemsetAsync(stats_dev, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
   IPT_CUDA(h->trace_counter.reserve(sizeof(unsigned long long)));
   IPT_CUDA(launch_trace_rays_stats(h->dev(), rays_dev, n, tri_dev, t_dev, (unsigned long long*)h->trace_counter.ptr, stats_dev, h->sm_count,
@@ -672,7 +748,7 @@ int iptTraceRays(void* scene, const float* rays, int n, int* tri, float* t) {
   if (!h) return -1;
   if (n < 0 || (n > 0 && (!rays || !tri || !t))) return fail("iptTraceRays: bad arguments");
   if (n == 0) return 0;
-  std::lock_guard<std::mutex> lk(h->mutex);
+  std::lock_guard<std::recursive_mutex> lk(h->mutex);
   IPT_CUDA(cudaSetDevice(h->device));
   IPT_CUDA(h->rays.reserve((size_t)n * 6 * sizeof(float)));
   IPT_CUDA(h->hits_tri.reserve((size_t)n * sizeof(int)));
@@ -692,6 +768,7 @@ int iptRenderDevice(void* scene, const IptRenderParams* p, float* img_dev, unsig
   Plan plan;
   if (make_plan(h, p, &plan) != 0) return -1;
   IPT_CUDA(cudaSetDevice(h->device));
+  CallGuard guard(h, (cudaStream_t)stream);
   return launch_forward(h, plan, img_dev, img8_dev, counters_dev, (cudaStream_t)stream);
 }
 
@@ -700,7 +777,7 @@ int iptRender(void* scene, const IptRenderParams* p, float* img, unsigned char* 
   if (!h) return -1;
   Plan plan;
   if (make_plan(h, p, &plan) != 0) return -1;
-  std::lock_guard<std::mutex> lk(h->mutex);
+  std::lock_guard<std::recursive_mutex> lk(h->mutex);
   IPT_CUDA(cudaSetDevice(h->device));
   const size_t n3 = (size_t)plan.rp.n_pix * 3;
   IPT_CUDA(h->img.reserve(n3 * sizeof(float)));
@@ -744,6 +821,7 @@ int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsign
   Plan plan;
   if (make_plan(h, p, &plan) != 0) return -1;
   IPT_CUDA(cudaSetDevice(h->device));
+  CallGuard guard(h, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   const DevScene sc = h->dev();
   const int nT = sc.nT;
@@ -836,7 +914,7 @@ int iptCreateGraphEx(void* scene, const IptRenderParams* p, const unsigned char*
   SceneHandle* h = checked_device(scene);
   if (!h) return -1;
   if (!p || !target) return fail("iptCreateGraphEx: bad arguments");
-  std::lock_guard<std::mutex> lk(h->mutex);
+  std::lock_guard<std::recursive_mutex> lk(h->mutex);
   IPT_CUDA(cudaSetDevice(h->device));
   const int nT = (int)h->host.tris.size();
   const size_t n_edges = (size_t)(nT + 1) * nT;
@@ -884,6 +962,7 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
   Plan plan;
   if (make_plan(h, &q, &plan) != 0) return -1;
   IPT_CUDA(cudaSetDevice(h->device));
+  CallGuard guard(h, (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   const DevScene sc = h->dev();
   const DevRender& rp = plan.rp;
@@ -900,57 +979,14 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
   const double inv_n = 1.0 / (3.0 * (double)rp.width * (double)rp.height);
   IPT_CUDA(launch_loss_dldpx(img, target_dev, rp.row_begin, rp.row_step, rp.width, rp.n_pix, inv_n, 1.0f / (float)rp.spp, (float*)h->dldpx.ptr, lossgrad_dev, st));
   g_launches += 1;
-  if (nT == 0) return 0;
-  unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
-  IPT_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
-  DevOut out;
-  memset(&out, 0, sizeof(out));
-  out.work_counter = reinterpret_cast<unsigned*>(ctr + 4);
-  out.counters = ctr;
-  out.target = target_dev;
-  out.dldpx = (const float*)h->dldpx.ptr;
-  out.acc_stride = 3 * nT;
-  // gradient tiles: one [3 nT] float tile per block in global memory, updated with fire-and-forget float
-  // reductions (shared-memory float atomics are compare-and-swap loops on this architecture); scenes whose
-  // tiles would be too large fall back to double atomics on the result itself
-  const char* acc_env = getenv("IPT_GRAD_ACC");   // developer A/B: 0 = global double, 1 = shared tile, 2 = global tile
-  size_t smem = paths_smem_bytes(sc, 0);
-  out.acc_in_smem = (3 * (size_t)nT <= 65536) ? 2 : 0;
-  if (acc_env && *acc_env) out.acc_in_smem = atoi(acc_env);
-  if (out.acc_in_smem == 1) smem = paths_smem_bytes(sc, 3 * nT);
-  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, sc, smem);
-  if (out.acc_in_smem) {
-    IPT_CUDA(h->block_acc.reserve((size_t)grid * 3 * nT * sizeof(float)));
-    out.block_acc = (float*)h->block_acc.ptr;
-    if (out.acc_in_smem == 2) IPT_CUDA(cudaMemsetAsync(out.block_acc, 0, (size_t)grid * 3 * nT * sizeof(float), st));
-  } else {
-    out.global_acc = lossgrad_dev + 1;
-  }
-  // adjoint vertex stacks: two halves of max_depth 32-byte vertices per resident thread (no initialisation needed:
-  // a sweep only reads what its own path wrote)
-  out.vdepth = q.max_depth;
-  IPT_CUDA(h->vstacks.reserve((size_t)grid * paths_block_threads() * 2 * (size_t)out.vdepth * 32));
-  out.vstacks = (float4*)h->vstacks.ptr;
-  {
-    const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
-    IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
-    IPT_CUDA(launch_paths(MODE_GRAD_ID, sc, rp, out, grid, smem, st));
-    IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
-    h->ev_count++;
-  }
-  g_launches += 1;
-  if (out.acc_in_smem) {
-    IPT_CUDA(launch_reduce_blocks(out.block_acc, grid, 3 * nT, lossgrad_dev + 1, 0, 0, st));
-    g_launches += 1;
-  }
-  return 0;
+  return launch_grad_pass(h, plan, target_dev, lossgrad_dev, st);
 }
 
 int iptRenderGrad(void* scene, const IptRenderParams* p, const unsigned char* target, double* loss, double* grad, float* img) {
   SceneHandle* h = checked_device(scene);
   if (!h) return -1;
   if (!p || !target || !loss || !grad) return fail("iptRenderGrad: bad arguments");
-  std::lock_guard<std::mutex> lk(h->mutex);
+  std::lock_guard<std::recursive_mutex> lk(h->mutex);
   IPT_CUDA(cudaSetDevice(h->device));
   const int nT = (int)h->host.tris.size();
   Plan plan;

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <memory>
 #include <string>
 
 #include "../../include/ipt_b200.h"
@@ -58,6 +59,7 @@ struct SceneHandle {
   int n_big = 0;
   bool use_bvh = false;
   bool host_only = false;
+  bool kd_dirty = false;      // the device albedos were changed on the device (iptSetMaterialsDevice, iptInverseStep): getMaterials reads them back
   // knobs copied from the loading thread's settings (iptSetTraversalMode / iptSetBvhLargeTriangleLimit / iptSetIntegrator)
   int traversal_mode = 0, big_max = 128, integrator = 0, wf_slots = 1 << 24;
   // ring of CUDA event pairs bracketing the last kEventRing k_paths launches (roofline timing without
@@ -68,7 +70,13 @@ struct SceneHandle {
   int* host_live = nullptr;          // pinned word for the wavefront integrator's live count
   Scratch wavefront;
   Scratch partial, counters, cnt_out, trace_counter, block_acc, vstacks, acc, dldpx, img, img8, target, raw, lossgrad, rays, hits_tri, hits_t;
-  std::mutex mutex;
+  // One call at a time per scene: every entry point holds `mutex` while it enqueues (the scratch buffers, the work
+  // counter and the event ring are per handle), and calls enqueued on DIFFERENT streams are chained through `busy`
+  // (recorded after each call, waited on by the next), so two calls in flight on one scene cannot share scratch.
+  std::recursive_mutex mutex;
+  cudaEvent_t busy = nullptr;
+  bool busy_recorded = false;
+  cudaStream_t busy_stream = nullptr;
 
   DevScene dev() const {
     DevScene d;
@@ -85,8 +93,29 @@ struct SceneHandle {
     Scratch* all[] = {&wavefront, &partial, &counters, &cnt_out, &trace_counter, &block_acc, &vstacks, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
     for (Scratch* s : all) s->release();
     if (host_live) cudaFreeHost(host_live);
+    if (busy) cudaEventDestroy(busy);
     if (stream) cudaStreamDestroy(stream);
     for (int i = 0; i < kEventRing; i++) { if (ev_start[i]) cudaEventDestroy(ev_start[i]); if (ev_stop[i]) cudaEventDestroy(ev_stop[i]); }
+  }
+};
+
+// RAII guard of a device-pointer entry point: takes the handle's mutex, makes `st` wait for the scene's previous call
+// (if that ran on another stream) and records `busy` on `st` when the enqueue is done.  Inside a stream capture the
+// events are skipped (a capture may not wait on outside work); the captured graph then owns the ordering.
+struct CallGuard {
+  SceneHandle* h;
+  cudaStream_t st;
+  std::unique_lock<std::recursive_mutex> lk;
+  bool capturing = false;
+  CallGuard(SceneHandle* h_, cudaStream_t st_) : h(h_), st(st_), lk(h_->mutex) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) capturing = true;
+    if (!capturing && h->busy && h->busy_recorded && h->busy_stream != st) cudaStreamWaitEvent(st, h->busy, 0);
+  }
+  ~CallGuard() {
+    if (!capturing && h->busy) {
+      if (cudaEventRecord(h->busy, st) == cudaSuccess) { h->busy_recorded = true; h->busy_stream = st; }
+    }
   }
 };
 
@@ -98,6 +127,10 @@ struct Plan {
   int rows;
 };
 int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan);
-int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev, cudaStream_t st);
+// forward pass of the shard into h->partial (+ toneMap into img_dev / img8_dev unless resolve == false)
+int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev, cudaStream_t st,
+                   bool resolve = true);
+// path adjoint of the shard: adds dLoss/dKd (3 nT doubles) to lossgrad_dev + 1; needs h->dldpx filled for this plan
+int launch_grad_pass(SceneHandle* h, const Plan& plan, const unsigned char* target_dev, double* lossgrad_dev, cudaStream_t st);
 
 }  // namespace ipt

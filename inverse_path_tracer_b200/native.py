@@ -19,6 +19,11 @@ class IptRenderParams(C.Structure):
                 ("group_samples", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("row_step", C.c_int)]
 
 
+class IptInverseConfig(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("kd_min", C.c_float), ("kd_max", C.c_float),
+                ("rank", C.c_int), ("world", C.c_int), ("timeout_ms", C.c_int)]
+
+
 def library_path():
     return _LIB_PATH
 
@@ -33,7 +38,9 @@ EXPORTS = ["loadScene", "freeScene", "createImage", "createGraph", "getMaterials
            "iptGraphCompress", "iptRenderGrad", "iptRenderGradDevice", "iptSetMaterialsDevice", "iptBuildBVH",
            "iptWritePNG", "iptReadPNG", "iptKernelLaunchCount", "iptPathKernelTimes", "iptLastCounters", "iptSetBvhBuilder", "iptTraceRaysStatsDevice",
            "iptSetIntegrator", "iptSceneSetIntegrator", "iptMeasureCopyGBps",
-           "iptSetBvhLargeTriangleLimit", "iptSceneLargeTriangles", "iptGraphCompressDevice"]
+           "iptSetBvhLargeTriangleLimit", "iptSceneLargeTriangles", "iptGraphCompressDevice",
+           "iptInverseDefaultConfig", "iptInverseCreate", "iptInverseMailbox", "iptInverseConnect", "iptInverseSetKd", "iptInverseStep",
+           "iptInverseState", "iptInverseDestroy"]
 
 
 def lib():
@@ -75,6 +82,13 @@ def lib():
         L.iptSetAssetRoot.argtypes = [C.c_char_p]
         L.iptPathKernelTimes.argtypes = [vp, vp, C.c_int]
         L.iptLastCounters.argtypes = [vp, vp]
+        L.iptInverseCreate.argtypes = [vp, vp, vp, vp, vp]
+        L.iptInverseMailbox.argtypes = [vp, vp, vp]
+        L.iptInverseConnect.argtypes = [vp, vp, vp]
+        L.iptInverseSetKd.argtypes = [vp, vp, C.c_int]
+        L.iptInverseStep.argtypes = [vp, C.c_ulonglong, C.c_int]
+        L.iptInverseState.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+        L.iptInverseDestroy.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -296,3 +310,70 @@ def graph_compress(raw, nT):
     data = np.zeros(7 * (nT + 1) * nT, np.float32)
     _check(lib().iptGraphCompress(_ptr(raw), nT, _ptr(data)), "iptGraphCompress")
     return data
+
+
+class InverseOptimizer:
+    """The inverse loop inside the library (include/ipt_b200.h part 3): Adam on the scene's nT x 3 albedos against a
+    target image, one call per iteration (or per batch of iterations), on this GPU's row shard.
+
+    `target_dev_ptr`: device address of the height x width x 3 uint8 target on the scene's GPU (the caller keeps the
+    buffer alive).  world > 1: exchange `ipc_handle()` between the ranks and call `connect_ipc(handles)` (one process
+    per GPU) or `connect_local([mailbox pointers])` (several ranks in one process)."""
+
+    def __init__(self, scene, params, target_dev_ptr, rank=0, world=1, lr=0.02, beta1=0.9, beta2=0.999, eps=1e-8, kd_min=1e-3, kd_max=1.0, timeout_ms=10000):
+        L = lib()
+        cfg = IptInverseConfig()
+        L.iptInverseDefaultConfig(C.byref(cfg))
+        cfg.lr, cfg.beta1, cfg.beta2, cfg.eps, cfg.kd_min, cfg.kd_max = lr, beta1, beta2, eps, kd_min, kd_max
+        cfg.rank, cfg.world, cfg.timeout_ms = int(rank), int(world), int(timeout_ms)
+        self.scene, self.nT, self.rank, self.world = scene, scene.nT, int(rank), int(world)
+        h = C.c_void_p(0)
+        _check(L.iptInverseCreate(scene.h, C.byref(params), C.c_void_p(int(target_dev_ptr)), C.byref(cfg), C.byref(h)), "iptInverseCreate")
+        self.h = h
+
+    def mailbox(self):
+        p = C.c_void_p(0)
+        _check(lib().iptInverseMailbox(self.h, C.byref(p), None), "iptInverseMailbox")
+        return p.value
+
+    def ipc_handle(self):
+        buf = (C.c_ubyte * 64)()
+        _check(lib().iptInverseMailbox(self.h, None, buf), "iptInverseMailbox")
+        return bytes(buf)
+
+    def connect_local(self, mailboxes):
+        arr = (C.c_void_p * self.world)(*[C.c_void_p(m) for m in mailboxes])
+        _check(lib().iptInverseConnect(self.h, arr, None), "iptInverseConnect")
+
+    def connect_ipc(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        _check(lib().iptInverseConnect(self.h, None, blob), "iptInverseConnect")
+
+    def set_kd(self, kd, reset_moments=True):
+        kd = np.ascontiguousarray(kd, np.float32).reshape(self.nT, 3)
+        _check(lib().iptInverseSetKd(self.h, _ptr(kd), 1 if reset_moments else 0), "iptInverseSetKd")
+
+    def step(self, first_seed, n_steps=1):
+        """enqueue n_steps iterations (seeds first_seed, first_seed + 1, ...); asynchronous"""
+        _check(lib().iptInverseStep(self.h, int(first_seed), int(n_steps)), "iptInverseStep")
+
+    def state(self, history=0):
+        """wait, then (loss of the last step, albedos [nT, 3], steps applied[, the last `history` losses])"""
+        loss = C.c_double(0)
+        steps = C.c_ulonglong(0)
+        kd = np.zeros((self.nT, 3), np.float32)
+        hist = np.zeros(max(history, 1), np.float64)
+        _check(lib().iptInverseState(self.h, C.byref(loss), _ptr(kd), C.byref(steps), _ptr(hist) if history else None, int(history)), "iptInverseState")
+        return (loss.value, kd, int(steps.value), hist[:history]) if history else (loss.value, kd, int(steps.value))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            lib().iptInverseDestroy(self.h)
+            self.h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -127,3 +127,22 @@ def render_loss(kd, tscene, params, target_u8, group=None, reduce=True):
     """reduce=True: `params` describes this rank's row shard of ONE scene, loss and gradient are summed over the
     ranks of `group`.  reduce=False: the scene belongs to this rank alone (scene-sharded batches, BASELINE config 4)."""
     return RenderLoss.apply(kd, tscene, params, target_u8, group, reduce)
+
+
+def inverse_optimizer(tscene, params, target_u8, group=None, **adam):
+    """native.InverseOptimizer for `tscene` (BASELINE config 3 / 4): the whole iteration -- render, loss, adjoint, sum
+    over the ranks of `group`, Adam, albedo update -- runs inside the library, enqueued by one call.  `params` describes
+    this rank's row shard; with an initialised process group of more than one rank the mailboxes are exchanged once
+    (CUDA IPC handles through all_gather_object) and every later step talks GPU to GPU over NVLink."""
+    assert target_u8.dtype == torch.uint8 and target_u8.is_cuda and target_u8.is_contiguous()
+    rank, world = 0, 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+    opt = native.InverseOptimizer(tscene.scene, params, target_u8.data_ptr(), rank=rank, world=world, **adam)
+    opt._target_keepalive = target_u8
+    if world > 1:
+        handles = [None] * world
+        torch.distributed.all_gather_object(handles, opt.ipc_handle(), group=group)
+        opt.connect_ipc(handles)
+        torch.distributed.barrier(group=group)
+    return opt

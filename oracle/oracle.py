@@ -41,12 +41,43 @@ def build(force=False):
 
 
 _lib = None
+_lib_kind = "-O2 -march=x86-64-v3 (portable build, oracle/Makefile)"
+NATIVE_DIR = os.path.join(HERE, "_native")
+
+
+def use_native_build():
+    """Timing legs of bench.py only: rebuild the oracle ON THIS HOST with -O3 -march=native into
+    oracle/_native/ (git- and gpurun-ignored: a -march=native binary must not travel between machines) and load that
+    one.  Same source, -ffp-contract=off, so the results are the same bits.  Falls back to the portable build when no
+    compiler is at hand.  Must be called before the first lib() / OracleScene."""
+    global LIB_PATH, _lib_kind
+    if _lib is not None:
+        return _lib_kind
+    out = os.path.join(NATIVE_DIR, "libipt_oracle_native.so")
+    src = os.path.join(HERE, "ipt_oracle.cpp")
+    try:
+        if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            os.makedirs(NATIVE_DIR, exist_ok=True)
+            subprocess.check_call([os.environ.get("CXX", "g++"), "-O3", "-march=native", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC",
+                                   "-pthread", "-shared", "-o", out, src], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        LIB_PATH = out
+        _lib_kind = "-O3 -march=native, built on this host"
+    except (OSError, subprocess.CalledProcessError):
+        pass
+    return _lib_kind
+
+
+def build_kind():
+    return _lib_kind
 
 
 def lib():
     global _lib
     if _lib is None:
-        build()
+        if LIB_PATH.startswith(NATIVE_DIR):
+            pass
+        else:
+            build()
         L = C.CDLL(LIB_PATH)
         L.orc_load_scene.restype = C.c_void_p
         L.orc_load_scene.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_char_p]
