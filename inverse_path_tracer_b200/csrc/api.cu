@@ -349,7 +349,7 @@ int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan) {
   int gs = p->group_samples;
   if (gs < 0) {   // auto (include/ipt_b200.h): depends on the full image size only
     gs = 64;
-    while (gs > 4 && (long long)p->width * p->height * p->spp < ((long long)gs << 20)) gs >>= 1;
+    while (gs > 1 && (long long)p->width * p->height * p->spp < ((long long)gs << 22)) gs >>= 1;
   }
   rp.group_samples = (gs <= 0 || gs > p->spp) ? p->spp : gs;
   rp.groups = (p->spp + rp.group_samples - 1) / rp.group_samples;
@@ -386,7 +386,7 @@ int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned ch
   out.partial = (float*)h->partial.ptr;
   if ((sc.use_bvh && h->integrator != 1) || (!sc.use_bvh && h->integrator == 2)) {
     // large scenes: wavefront (wavefront.cu); batches of at most `cap` paths
-    const long long total = (long long)rp.n_pix * std::min(rp.spp, rp.group_samples);
+    const long long total = (long long)rp.n_pix * rp.spp;
     const int cap = (int)std::max<long long>(1, std::min<long long>(total, (long long)h->wf_slots));
     IPT_CUDA(h->wavefront.reserve(wavefront_workspace_bytes(cap)));
     if (!h->host_live) IPT_CUDA(cudaHostAlloc((void**)&h->host_live, sizeof(int), cudaHostAllocDefault));

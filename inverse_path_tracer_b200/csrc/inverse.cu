@@ -209,6 +209,18 @@ static int enqueue_step(InverseHandle* o, unsigned long long seed) {
   if (q.max_depth <= 0 || q.max_depth > kGradMaxDepth) q.max_depth = kGradMaxDepth;
   Plan plan;
   if (make_plan(h, &q, &plan) != 0) return -1;
+  if (o->params.group_samples < 0) {
+    // The size rule looks at the whole image so that shards of a RENDER agree bit for bit; here only sums over the
+    // shard matter (the exchange step re-associates them anyway), so a small shard -- one of eight ranks has ~20 paths
+    // per resident lane -- takes groups small enough for >= 16 work items per lane: the launch must not end in a tail
+    const long long lanes = (long long)h->sm_count * 5 * paths_block_threads();
+    int gs = plan.rp.group_samples;
+    while (gs > 1 && (long long)plan.rp.n_pix * plan.rp.spp / gs < 16 * lanes) gs >>= 1;
+    if (gs != plan.rp.group_samples) {
+      q.group_samples = gs;
+      if (make_plan(h, &q, &plan) != 0) return -1;
+    }
+  }
   const DevRender& rp = plan.rp;
   const size_t n3 = (size_t)rp.n_pix * 3;
   IPT_CUDA(h->dldpx.reserve(n3 * sizeof(float)));

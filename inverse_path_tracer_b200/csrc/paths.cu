@@ -40,6 +40,14 @@ __device__ __forceinline__ int adj_light(const AdjVertex& v) { return __float_as
 #ifndef IPT_MINB
 #define IPT_MINB 5
 #endif
+// Camera rays are generated AHEAD of their use (profiles/r02_*: path regeneration ran every trip of the loop with ~9 of 32
+// lanes, 120 instructions): every lane owns a ring of kRing finished camera rays of its upcoming samples in shared memory;
+// when a lane that needs a ray finds its ring empty, ALL lanes with a free slot generate one (so generation runs once per
+// ~2.4 trips at ~22 lanes) and taking a ray is one 16-byte load.  Entry = {direction, work item}; the generator's own
+// cursor (pixel, row / column, next sample, end) lives in two more shared-memory slots of the lane.
+constexpr int kRing = 4;
+constexpr int kRingF4 = kRing + 2;
+constexpr uint32_t kRingStride = kBlock * 16u;   // bytes between two slots of one thread
 // BVH is a compile-time flag: in brute-force mode every scene access is a shared-memory access with 32-bit
 // addressing (a runtime choice between shared and global pointers forces generic loads)
 // PLAIN is a compile-time promise that no triangle has per-vertex normals or a specular lobe (true for every
@@ -71,9 +79,11 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   const int nT = sc.nT, nE = sc.nE;
   SmallScene ss;
   ss.nGroups = 0;
-  float4* cursor = smem;
-  int* bvh_stack = reinterpret_cast<int*>(smem);
-  if (BVH) cursor = smem + (sc.bvh_depth * kBlock + 3) / 4;   // one stack column per thread, as deep as the tree
+  // per-thread camera-ray ring + generator state (see [B]): kRingF4 float4 columns, slot k of thread t at [k * kBlock + t]
+  const uint32_t ring_a = smem_addr(smem) + threadIdx.x * 16u;
+  float4* cursor = smem + kRingF4 * kBlock;
+  int* bvh_stack = reinterpret_cast<int*>(cursor);
+  if (BVH) cursor += (sc.bvh_depth * kBlock + 3) / 4;   // one stack column per thread, as deep as the tree
   // brute-force set: the whole scene, or in BVH mode the large triangles kept out of the tree
   if (!BVH || sc.nGroups > 0) ss = stage_small_scene(sc, cursor, &cursor);
   float4* smat = cursor;
@@ -104,14 +114,25 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   const f3 zero3 = mk3(0.0f, 0.0f, 0.0f);
 
   // ---- work item bookkeeping -------------------------------------------------------------------
-  bool have_item = false, exhausted = false;
-  unsigned item = 0;
-  int pixel = 0;
-  float pix_c = 0.0f, pix_r = 0.0f;   // column / row of the item's pixel, as floats (one integer division per item)
-  int s_next = 0, s_end = 0;      // next sample of the item to start / one past its last sample
+  unsigned item = 0xffffffffu;    // work item (pixel, sample group) whose samples this lane is tracing
+  int pixel = 0;                  // its global pixel index (RNG counter, target lookup)
   int fin_left = 0;               // samples of the item not yet finalised
   int cur_s = 0;                  // sample index of the path in flight (RNG counter)
   float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
+  int rhead = 0, rcount = 0;      // camera-ray ring: first entry, entries
+  bool g_done = false;            // the generator found the work queue empty
+  sts4(ring_a + (kRing + 1) * kRingStride, make_float4(0.0f, 0.0f, 0.0f, 0.0f));   // generator cursor {next sample, end sample, next item, end of the claimed run}: all "used up"
+  unsigned claim_base = 0;        // queue position this warp saw at its last claim (sizes the next one)
+  const unsigned claim_div = gridDim.x * blockDim.x * 2u;
+  // floor(i / groups) and floor(pixel / width) by multiplication with ceil(2^64 / d) (exact below 2^32)
+  auto decode_item = [&](unsigned my, int& pix_local, int& g, int& px, int& r, int& c) {
+    pix_local = rp.groups == 1 ? (int)my : (int)__umul64hi((unsigned long long)my, rp.magic_groups);
+    g = (int)(my - (unsigned)pix_local * (unsigned)rp.groups);
+    const int lr = rp.width == 1 ? pix_local : (int)__umul64hi((unsigned long long)pix_local, rp.magic_width);
+    c = pix_local - lr * rp.width;
+    r = rp.row_begin + lr * rp.row_step;       // interleaved row shards
+    px = r * rp.width + c;                     // global pixel index
+  };
   // ---- path state ----------------------------------------------------------------------------------
   bool active = false;            // `h` holds the closest hit of this path's extension ray
   HitRec h;
@@ -220,7 +241,60 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         float* dst = out.partial + (size_t)item * 3;
         dst[0] = part0; dst[1] = part1; dst[2] = part2;
       }
-      have_item = false;
+    }
+  };
+
+  // one round of camera-ray generation: every lane with a free ring slot makes the ray of its next sample (path_trace.cu:
+  // 155-165, Ray::transform scene_basics.h:307-319), claiming its next work item first when the current one is used up
+  // (one warp-aggregated atomic).  Called by the whole warp.
+  auto generate_round = [&]() {
+    const bool gen = !g_done && rcount < kRing;
+    float4 ga = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    int s_nx = 0, s_en = 0;
+    unsigned it_next = 0, it_end = 0;
+    if (gen) {
+      ga = lds4(ring_a + kRing * kRingStride);           // {pixel, column, row, item}
+      const float4 gb = lds4(ring_a + (kRing + 1) * kRingStride);
+      s_nx = __float_as_int(gb.x); s_en = __float_as_int(gb.y);
+      it_next = __float_as_uint(gb.z); it_end = __float_as_uint(gb.w);
+    }
+    const bool fresh = gen && s_nx == s_en;              // the generator's item is used up: next item of its run, or a new claim
+    const bool claim = fresh && it_next >= it_end;
+    const unsigned fm = __ballot_sync(kFull, claim);
+    if (fm) {
+      // guided self-scheduling: a claim is a run of n consecutive items per lane, n shrinking from 8 to 1 as the queue
+      // empties (few atomics while there is plenty of work, single items at the end so the launch does not end in a tail)
+      const unsigned remaining = n_items > claim_base ? n_items - claim_base : 0u;
+      const unsigned n = min(max(remaining / claim_div, 1u), 8u);
+      const int leader = __ffs(fm) - 1;
+      unsigned base = 0;
+      if ((int)lane == leader) base = atomicAdd(out.work_counter, (unsigned)__popc(fm) * n);   // overshoot <= 8 per lane: no wrap (make_plan)
+      base = __shfl_sync(kFull, base, leader);
+      claim_base = base;
+      if (claim) {
+        it_next = base + (unsigned)__popc(fm & ((1u << lane) - 1u)) * n;
+        it_end = min(it_next + n, n_items);
+        if (it_next >= n_items) g_done = true;
+      }
+    }
+    if (fresh && !g_done) {
+      const unsigned my = it_next++;
+      int pix_local, g, px, r, c;
+      decode_item(my, pix_local, g, px, r, c);
+      s_nx = g * rp.group_samples;
+      s_en = min(rp.spp, s_nx + rp.group_samples);
+      ga = make_float4(__int_as_float(px), (float)c, (float)r, __uint_as_float(my));
+      sts4(ring_a + kRing * kRingStride, ga);
+    }
+    if (gen && !g_done) {
+      const u4 rn = philox4x32_10((uint32_t)__float_as_int(ga.x), (uint32_t)s_nx, 0u, IPT_STREAM_CAMERA, rp.keys);
+      const float x = fmaf(ga.y + u01(rn.x), rp.two_over_w, -1.0f);
+      const float y = fmaf(ga.z + u01(rn.y), -rp.two_over_h, 1.0f);
+      const f3 dl = mk3(x, y, 1.0f);
+      const f3 dir = IPT_NORMALIZE(mk3(dot3(sc.cam[0], sc.cam[1], sc.cam[2], dl), dot3(sc.cam[4], sc.cam[5], sc.cam[6], dl), dot3(sc.cam[8], sc.cam[9], sc.cam[10], dl)));
+      sts4(ring_a + (uint32_t)((rhead + rcount) & (kRing - 1)) * kRingStride, make_float4(dir.x, dir.y, dir.z, ga.w));
+      rcount++;
+      sts4(ring_a + (kRing + 1) * kRingStride, make_float4(__int_as_float(s_nx + 1), __int_as_float(s_en), __uint_as_float(it_next), __uint_as_float(it_end)));
     }
   };
 
@@ -374,35 +448,24 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     }
 
     // =========== [B] path regeneration: lanes without an extension ray start their next sample ========
-    // A lane whose path is ending but still waits for its last shadow ray (end_after) may already start
-    // the next sample of the SAME item; at an item boundary it idles one trip (once per 64 samples).
+    // A lane whose path is ending but still waits for its last shadow ray (end_after) may already start the next sample of
+    // the SAME item; at an item boundary it idles one trip (the partial sums still belong to the old item).
+    // (adjoint: no new sample while a finished path waits for its slot, and no early start of the next sample while the
+    //  other stack half is still being swept -- the ending path will have to wait in it)
     {
-      const bool need = !ext_valid && !have_item && !exhausted && !end_after && !(MODE == MODE_GRAD && fin_wait);
-      const unsigned need_mask = __ballot_sync(kFull, need);
-      if (need_mask) {
-        const int leader = __ffs(need_mask) - 1;
-        unsigned base = 0;
-        if ((int)lane == leader) base = atomicAdd(out.work_counter, (unsigned)__popc(need_mask));   // overshoot <= one claim per lane: no wrap
-        base = __shfl_sync(kFull, base, leader);
-        if (need) {
-          const unsigned my = base + __popc(need_mask & ((1u << lane) - 1u));
-          if (my < n_items) {
-            have_item = true;
-            item = my;
-            // floor(my / groups) and floor(pixel / width) by multiplication with ceil(2^64 / d) (exact below 2^32)
-            const int pix_local = rp.groups == 1 ? (int)my : (int)__umul64hi((unsigned long long)my, rp.magic_groups);
-            const int g = (int)(my - (unsigned)pix_local * (unsigned)rp.groups);
-            {
-              const int lr = rp.width == 1 ? pix_local : (int)__umul64hi((unsigned long long)pix_local, rp.magic_width);
-              const int c = pix_local - lr * rp.width;
-              const int r = rp.row_begin + lr * rp.row_step;       // interleaved row shards
-              pixel = r * rp.width + c;                            // global pixel index: RNG counter, target lookup
-              pix_r = (float)r;
-              pix_c = (float)c;
-            }
-            s_next = g * rp.group_samples;
-            s_end = min(rp.spp, s_next + rp.group_samples);
-            fin_left = s_end - s_next;
+      const bool want = !ext_valid && !(MODE == MODE_GRAD && (fin_wait || (end_after && sw_k >= 0)));
+      if (__ballot_sync(kFull, want && rcount == 0 && !g_done)) generate_round();
+      if (want && rcount > 0) {
+        const float4 e = lds4(ring_a + (uint32_t)rhead * kRingStride);
+        const unsigned e_item = __float_as_uint(e.w);
+        const bool new_item = e_item != item;
+        if (!new_item || (fin_left == 0 && !end_after)) {
+          if (new_item) {
+            int pix_local, g, r, c;
+            decode_item(e_item, pix_local, g, pixel, r, c);
+            item = e_item;
+            cur_s = g * rp.group_samples - 1;
+            fin_left = min(rp.spp, (g + 1) * rp.group_samples) - g * rp.group_samples;
             part0 = part1 = part2 = 0.0f;
             if (MODE != MODE_RENDER) {
               const unsigned char* tp = out.target + (size_t)pixel * 3;
@@ -412,32 +475,23 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
               const float* wp = out.dldpx + (size_t)pix_local * 3;
               w0 = wp[0]; w1 = wp[1]; w2 = wp[2];
             }
-          } else {
-            exhausted = true;
           }
+          cur_s++;
+          rhead = (rhead + 1) & (kRing - 1);
+          rcount--;
+          rpos = mk3(sc.cam[3], sc.cam[7], sc.cam[11]);
+          rdir = xyz(e);
+          m0 = m1 = m2 = 1.0f;
+          bounce = 0;
+          gweight = 1.0f;
+          gdst = nT;
+          if (!end_after) { q0 = q1 = q2 = 1.0f; L0 = L1 = L2 = 0.0f; e_tri = -1; d0 = d1 = d2 = 0.0f; }
+          ext_valid = true;
+          n_paths++;
         }
       }
     }
-    // (adjoint: no new sample while a finished path waits for its slot, and no early start of the next sample while the
-    //  other stack half is still being swept -- the ending path will have to wait in it)
-    if (!ext_valid && have_item && s_next < s_end && !(MODE == MODE_GRAD && (fin_wait || (end_after && sw_k >= 0)))) {
-      // camera ray (path_trace.cu:155-165, Ray::transform scene_basics.h:307-319)
-      cur_s = s_next++;
-      const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, 0u, IPT_STREAM_CAMERA, rp.keys);
-      const float x = fmaf(pix_c + u01(rn.x), rp.two_over_w, -1.0f);
-      const float y = fmaf(pix_r + u01(rn.y), -rp.two_over_h, 1.0f);
-      const f3 dl = mk3(x, y, 1.0f);
-      rpos = mk3(sc.cam[3], sc.cam[7], sc.cam[11]);
-      rdir = IPT_NORMALIZE(mk3(dot3(sc.cam[0], sc.cam[1], sc.cam[2], dl), dot3(sc.cam[4], sc.cam[5], sc.cam[6], dl), dot3(sc.cam[8], sc.cam[9], sc.cam[10], dl)));
-      m0 = m1 = m2 = 1.0f;
-      bounce = 0;
-      gweight = 1.0f;
-      gdst = nT;
-      if (!end_after) { q0 = q1 = q2 = 1.0f; L0 = L1 = L2 = 0.0f; e_tri = -1; d0 = d1 = d2 = 0.0f; }
-      ext_valid = true;
-      n_paths++;
-    }
-    if (__all_sync(kFull, !ext_valid && !sh_valid && !have_item && exhausted)) break;
+    if (__all_sync(kFull, !ext_valid && !sh_valid && fin_left == 0 && rcount == 0 && g_done)) break;
     if (!ext_valid) rdir = zero3;   // (kept in the state itself: a select at the call is re-evaluated inside the group loop)
 
     // =========== [C] closest hits: extension ray and shadow ray ==========================================
@@ -666,7 +720,7 @@ __global__ void k_set_kd(float4* __restrict__ mat, const float* __restrict__ kd,
 // ------------------------------------------------------------------------------------------------
 
 size_t paths_smem_bytes(const DevScene& sc, int acc_floats) {
-  size_t b = (size_t)acc_floats * sizeof(float);
+  size_t b = (size_t)acc_floats * sizeof(float) + (size_t)kRingF4 * kBlock * sizeof(float4);   // accumulators + camera-ray rings
   if (!sc.use_bvh || sc.nE <= kLightSmemMax) b += (size_t)3 * sc.nE * sizeof(float4);
   if (!sc.use_bvh) b += small_scene_smem_bytes(sc.nStream) + (size_t)kMatStride * sc.nT * sizeof(float4);
   else b += bvh_stack_bytes(sc) + (sc.nGroups > 0 ? small_scene_smem_bytes(sc.nStream) : 0);

@@ -280,20 +280,28 @@ __global__ void __launch_bounds__(kWfBlock, IPT_WF_MINB) k_wf_shade(DevScene sc,
   }
 }
 
-// toneMap's running sum (path_trace.cu:190-193) over the batch: samples in order, continuing the group's partial sum
-__global__ void __launch_bounds__(kWfBlock) k_wf_accumulate(const float* __restrict__ lsamp, WfBatch b, int group, int groups, int first, float inv_spp,
+// toneMap's running sum (path_trace.cu:190-193) over the batch: samples in order, each into the partial sum of its
+// sample group (a batch may start inside a group -- it then continues that group's partial -- and span several groups)
+__global__ void __launch_bounds__(kWfBlock) k_wf_accumulate(const float* __restrict__ lsamp, WfBatch b, int group_samples, int groups, int spp, float inv_spp,
                                                             float* __restrict__ partial) {
   const int pl = blockIdx.x * blockDim.x + threadIdx.x;
   if (pl >= b.tile_n) return;
-  float* dst = partial + ((size_t)(b.tile_p0 + pl) * groups + group) * 3;
-  float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
-  if (!first) { p0 = dst[0]; p1 = dst[1]; p2 = dst[2]; }
   const size_t cap = (size_t)b.cap;
-  for (int ss = 0; ss < b.ns; ss++) {
-    const size_t path = (size_t)ss * b.tile_n + pl;
-    p0 += lsamp[0 * cap + path] * inv_spp; p1 += lsamp[1 * cap + path] * inv_spp; p2 += lsamp[2 * cap + path] * inv_spp;
+  int ss = 0;
+  while (ss < b.ns) {
+    const int s = b.s0 + ss;
+    const int g = s / group_samples;
+    const int g_begin = g * group_samples, g_end = min(spp, g_begin + group_samples);
+    float* dst = partial + ((size_t)(b.tile_p0 + pl) * groups + g) * 3;
+    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+    if (s != g_begin) { p0 = dst[0]; p1 = dst[1]; p2 = dst[2]; }
+    const int n_here = min(b.ns - ss, g_end - s);
+    for (int k = 0; k < n_here; k++, ss++) {
+      const size_t path = (size_t)ss * b.tile_n + pl;
+      p0 += lsamp[0 * cap + path] * inv_spp; p1 += lsamp[1 * cap + path] * inv_spp; p2 += lsamp[2 * cap + path] * inv_spp;
+    }
+    dst[0] = p0; dst[1] = p1; dst[2] = p2;
   }
-  dst[0] = p0; dst[1] = p1; dst[2] = p2;
 }
 
 // ---- wavefront forward pass ------------------------------------------------------------------------------
@@ -329,12 +337,11 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
   const bool unbounded = rp.max_depth <= 0;
   for (int p0 = 0; p0 < rp.n_pix; p0 += tile_cap) {
     const int tn = std::min(tile_cap, rp.n_pix - p0);
-    const int nsb = std::max(1, std::min(rp.group_samples, cap / tn));
-    for (int g = 0; g < rp.groups; g++) {
-      const int g_begin = g * rp.group_samples, g_end = std::min(rp.spp, g_begin + rp.group_samples);
-      for (int s0 = g_begin; s0 < g_end; s0 += nsb) {
+    const int nsb = std::max(1, std::min(rp.spp, cap / tn));
+    {
+      for (int s0 = 0; s0 < rp.spp; s0 += nsb) {
         WfBatch b;
-        b.cap = cap; b.tile_p0 = p0; b.tile_n = tn; b.s0 = s0; b.ns = std::min(nsb, g_end - s0);
+        b.cap = cap; b.tile_p0 = p0; b.tile_n = tn; b.s0 = s0; b.ns = std::min(nsb, rp.spp - s0);
         const int n_paths = b.tile_n * b.ns;
         int cur = 0;
         k_wf_generate<<<std::min((n_paths + kWfBlock - 1) / kWfBlock, shade_grid), kWfBlock, 0, st>>>(sc, rp, b, state[0], rays[0], n_live + 0, counters);
@@ -357,7 +364,7 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
             if (*host_live == 0) break;
           }
         }
-        k_wf_accumulate<<<(b.tile_n + kWfBlock - 1) / kWfBlock, kWfBlock, 0, st>>>(lsamp, b, g, rp.groups, s0 == g_begin ? 1 : 0, rp.inv_spp, partial);
+        k_wf_accumulate<<<(b.tile_n + kWfBlock - 1) / kWfBlock, kWfBlock, 0, st>>>(lsamp, b, rp.group_samples, rp.groups, rp.spp, rp.inv_spp, partial);
         *n_launches += 1;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

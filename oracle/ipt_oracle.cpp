@@ -1129,7 +1129,7 @@ static inline int group_size(const Params& P) {
   int gs = P.group_samples;
   if (gs < 0) {
     gs = 64;
-    while (gs > 4 && (long long)P.width * P.height * P.spp < ((long long)gs << 20)) gs >>= 1;
+    while (gs > 1 && (long long)P.width * P.height * P.spp < ((long long)gs << 22)) gs >>= 1;
   }
   return (gs <= 0 || gs > P.spp) ? P.spp : gs;
 }

@@ -28,11 +28,31 @@ def main():
     ap.add_argument("--shards", type=int, default=8)
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--profile", type=int, default=1)
+    ap.add_argument("--impl", default="python", choices=["python", "library"], help="python: render_loss + torch Adam per iteration; library: iptInverseStep")
     a = ap.parse_args()
     from PIL import Image
     dev = torch.device("cuda", 0)
     sc = TorchScene(parse_scene_file(os.path.join(ASSETS, "scenes", "0.txt")), asset_root=ASSETS, device=0)
     target = torch.from_numpy(np.asarray(Image.open(os.path.join(ROOT, "tests", "golden", "golden_0_true.png")).convert("RGB")).copy()).to(dev)
+    if a.impl == "library":
+        # the whole iteration inside the library (csrc/inverse.cu): one C call enqueues `iters` iterations
+        from inverse_path_tracer_b200.torch_api import inverse_optimizer
+        p = ipt.default_params(width=500, height=500, spp=64, max_depth=0, row_begin=0, row_end=500, row_step=a.shards)
+        lopt = inverse_optimizer(sc, p, target, lr=0.02)
+        lopt.set_kd(np.full((sc.nT, 3), 0.5, np.float32))
+        lopt.step(1000, 5)
+        lopt.state()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        lopt.step(0, a.iters)
+        t_issue = time.perf_counter() - t0
+        loss, _, steps = lopt.state()
+        t_wall = time.perf_counter() - t0
+        print("shards %d [library]: %.3f ms/iter wall (%.3f ms/iter host issue time), loss %.6f after %d steps" % (
+            a.shards, 1e3 * t_wall / a.iters, 1e3 * t_issue / a.iters, loss, steps))
+        ms = sc.scene.kernel_times_ms(4)
+        print("last path-kernel launches (ms, newest first):", ["%.3f" % x for x in ms])
+        return
     kd = torch.full((sc.nT, 3), 0.5, device=dev, requires_grad=True)
     opt = torch.optim.Adam([kd], lr=0.02)
 
