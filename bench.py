@@ -124,11 +124,25 @@ def run_cpu_sample(O, osc, seed, rows, threads):
     return cnt, dt, (rb, re)
 
 
+def cpu_render_rate(O, osc, threads, reps=1, **kw):
+    """best of `reps` oracle renders: (Mrays/s, Mpaths/s, seconds, counters)"""
+    best = None
+    for i in range(reps):
+        P = O.make_params(seed=i, **kw)
+        t0 = time.perf_counter()
+        _, cnt = osc.render(P, threads=threads)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[2]:
+            best = ((cnt["ext_rays"] + cnt["shadow_rays"]) / dt / 1e6, cnt["paths"] / dt / 1e6, dt, cnt)
+    return best
+
+
 def reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
     from oracle import oracle as O
+    kind = O.use_native_build()
     osc = O.OracleScene(CORNELL, ASSETS)
     threads = O.hardware_threads() or 1
     rows = args.cpu_rows
@@ -143,8 +157,8 @@ def reference_arm(args):
         paths += cnt["paths"]
         total += dt
     v = rays / total / 1e6
-    sample = "rows [%d,%d) of the %dx%d image at %d spp per step (%d paths/step), %d host threads" % (
-        band[0], band[1], WORKLOAD["width"], WORKLOAD["height"], WORKLOAD["spp"], paths // max(args.steps, 1), threads)
+    sample = "rows [%d,%d) of the %dx%d image at %d spp per step (%d paths/step), %d host threads, oracle built %s" % (
+        band[0], band[1], WORKLOAD["width"], WORKLOAD["height"], WORKLOAD["spp"], paths // max(args.steps, 1), threads, kind)
     line = {"impl": "reference", "metric": "Mrays/s", "value": v, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -165,7 +179,7 @@ def b200_arm(args):
 
     import inverse_path_tracer_b200 as ipt
     from inverse_path_tracer_b200 import native, parallel
-    from inverse_path_tracer_b200.torch_api import TorchScene, render_loss
+    from inverse_path_tracer_b200.torch_api import TorchScene, inverse_optimizer, render_loss
 
     rank, world, local = dist_env()
     if world != args.gpus:
@@ -202,6 +216,19 @@ def b200_arm(args):
     nT = ts.nT
     rb, re, rstep = parallel.shard_rows_interleaved(w["height"], rank, world)   # rows rank, rank+N, ...: equal work per GPU
     rows = len(range(rb, re, rstep))
+    peaks, peak_kind = measured_peaks()
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    peak_tflops = sm_count * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    peak_source = "%s: %d SMs x 128 lanes x 2 x sm_max_mhz %.0f" % (peak_kind, sm_count, peaks["sm_max_mhz"])
+
+    def fp32_roofline(local_rays_per_launch, n_tris, kernel_ms, traffic=None, traffic_source=None):
+        ach = local_rays_per_launch * FLOP_PER_TEST * n_tris / (kernel_ms * 1e-3) / 1e12
+        r = {"bound": "fp32", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s", "frac": ach / peak_tflops, "traffic": traffic,
+             "peak_source": peak_source, "kernel_ms": kernel_ms,
+             "algorithmic": "%d FLOP per ray-triangle test x %d triangles per ray (SURVEY.md 8d)" % (FLOP_PER_TEST, n_tris)}
+        if traffic_source:
+            r["traffic_source"] = traffic_source
+        return r
 
     def params(seed, **kw):
         base = dict(width=w["width"], height=w["height"], spp=w["spp"], max_depth=w["max_depth"], p_rr=w["p_rr"],
@@ -245,27 +272,28 @@ def b200_arm(args):
     # roofline of the dominant kernel on this rank (rank 0 reports its own)
     local_rays = cnt[1] + cnt[2]
     k_ms = float(np.mean(kernel_ms)) if len(kernel_ms) else float("nan")
-    peaks, peak_kind = measured_peaks()
-    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-    peak_tflops = sm_count * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
-    achieved_tflops = (local_rays / max(args.steps, 1)) * FLOP_PER_TEST * nT / (k_ms * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic_k_paths_render.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1 and not args.small:
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_source = "constant from the committed ncu --set full capture of this launch (%s); not re-measured in this run" % tj.get("source", "profiles/")
         except Exception:
             traffic = None
+    roofline = fp32_roofline(local_rays / max(args.steps, 1), nT, k_ms, traffic, traffic_source)
 
     # ---- end to end through the host-buffer C ABI -------------------------------------------------------
-    host_img = np.empty((rows, w["width"], 3), np.float32)
+    host_img = torch.empty((rows, w["width"], 3), dtype=torch.float32, pin_memory=True).numpy()
     kd = ts.scene.get_materials()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(10, args.steps)
 
     def e2e_step(seed):
         ts.scene.set_materials(kd)                                      # H2D: this step's inputs (albedos)
         return ts.scene.render(params(seed), img=host_img)[1]           # D2H: the float image of this rank's rows
 
+    if args.small:
+        e2e_steps = 3
     e2e_step(20_000)
     barrier()
     t0 = time.perf_counter()
@@ -277,133 +305,163 @@ def b200_arm(args):
     e_dt = max_over_ranks(time.perf_counter() - t0)
     e_value = sum_over_ranks(e_rays) / e_dt / 1e6
 
-    # ---- headline point of BASELINE.json's metric: 512 x 512, 64 spp ------------------------------------
     extra = {"mpaths_per_s": paths / (ms * 1e-3) / 1e6, "rays_per_path": rays / max(paths, 1),
              "kernel_ms_mean": k_ms, "kernel_share_of_step": k_ms * args.steps / max(ms, 1e-9)}
     if not args.no_extras:
+        # ---- BASELINE.json's metric point: CornellBox 512 x 512, 64 spp (unbounded depth: the reference has no depth
+        #      limit) -- device-resident value, FP32 roofline of its kernel, end to end through iptRender, CPU oracle.
+        #      Each frame is timed by its own event pair; the L2 flush runs between frames, outside the timed intervals.
         hb, he, hs = parallel.shard_rows_interleaved(512, rank, world)
         hp = lambda s: ipt.default_params(width=512, height=512, spp=64, max_depth=0, seed=s, row_begin=hb, row_end=he, row_step=hs)
-        hout = torch.empty((len(range(hb, he, hs)), 512, 3), dtype=torch.float32, device=dev)
+        hrows = len(range(hb, he, hs))
+        hout = torch.empty((hrows, 512, 3), dtype=torch.float32, device=dev)
         for i in range(3):
             ts.render(hp(100 + i), out=hout, counters=counters)
         barrier()
         total.zero_()
-        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
-        h0.record()
+        reps = 20
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         for i in range(reps):
+            flush.zero_()
+            if world > 1:
+                dist.barrier()
+            evs[i][0].record()
             ts.render(hp(i), out=hout, counters=counters)
-            total.add_(counters)
             if world > 1:
                 parallel.gather_rows_interleaved(hout, 512)
-            flush.zero_()
-        h1.record()
+            evs[i][1].record()
+            total.add_(counters)
         barrier()
-        hms = max_over_ranks(h0.elapsed_time(h1))
+        hms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+        hk = ts.scene.kernel_times_ms(reps)
         hc = [int(x) for x in total.tolist()]
-        extra["cornell_512x512_64spp_unbounded"] = {"mrays_per_s": sum_over_ranks(hc[1] + hc[2]) / (hms * 1e-3) / 1e6,
-                                                     "mpaths_per_s": sum_over_ranks(hc[0]) / (hms * 1e-3) / 1e6, "ms_per_frame": hms / reps}
-        # ---- inverse iterations/s (BASELINE config 3): scenes/0.txt, 500x500, 64 spp/iter, Adam on 30x3 albedos
+        h_rays, h_paths = sum_over_ranks(hc[1] + hc[2]), sum_over_ranks(hc[0])
+        point = {"mrays_per_s": h_rays / (hms * 1e-3) / 1e6, "mpaths_per_s": h_paths / (hms * 1e-3) / 1e6, "ms_per_frame": hms / reps,
+                 "timing": "sum of %d per-frame CUDA-event intervals (render%s), max over ranks; 256 MiB L2 flush between frames, outside the intervals" % (
+                     reps, " + all-gather" if world > 1 else ""),
+                 "roofline": fp32_roofline((hc[1] + hc[2]) / reps, nT, float(np.mean(hk)))}
+        # end to end: host buffers in, host image out
+        hhost = torch.empty((hrows, 512, 3), dtype=torch.float32, pin_memory=True).numpy()
+
+        def h_e2e(seed):
+            ts.scene.set_materials(kd)
+            return ts.scene.render(hp(seed), img=hhost)[1]
+        h_e2e(99)
+        barrier()
+        t0 = time.perf_counter()
+        he_rays = 0
+        for i in range(20):
+            c = h_e2e(i)
+            he_rays += c["ext_rays"] + c["shadow_rays"]
+        torch.cuda.synchronize()
+        he_dt = max_over_ranks(time.perf_counter() - t0)
+        point["e2e"] = {"value": sum_over_ranks(he_rays) / he_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(nT * 3 * 4),
+                        "d2h_bytes_per_step": int(hrows * 512 * 3 * 4 + 24), "steps": 20, "ms_per_frame": 1e3 * he_dt / 20}
+        extra["metric_point_cornell_512x512_64spp_unbounded"] = point
+
+        # ---- inverse iterations/s (BASELINE config 3): scenes/0.txt, 500x500 target, 64 spp / iteration, Adam on the 30x3
+        #      albedos, rows interleaved over the ranks.  The whole iteration runs inside the library (csrc/inverse.cu:
+        #      render, loss, adjoint, GPU-to-GPU exchange of [loss, gradient] over NVLink, Adam) -- one C call per batch.
         from inverse_path_tracer_b200.ipt_cuda import parse_scene_file
         objs = parse_scene_file(os.path.join(ASSETS, "scenes", "0.txt"))
         inv = TorchScene(objs, asset_root=ASSETS, device=local)
         from PIL import Image
         target = torch.from_numpy(np.asarray(Image.open(os.path.join(ROOT, "tests", "golden", "golden_0_true.png")).convert("RGB")).copy()).to(dev)
         ib, ie, istep = parallel.shard_rows_interleaved(500, rank, world)   # 500 rows: shards may differ by one row; only sums are exchanged
-        kd_param = torch.full((inv.nT, 3), 0.5, device=dev, requires_grad=True)
-        opt = torch.optim.Adam([kd_param], lr=0.02)
-
-        def inv_iter(it):
-            opt.zero_grad(set_to_none=True)
-            p = ipt.default_params(width=500, height=500, spp=64, max_depth=0, seed=it, row_begin=ib, row_end=ie, row_step=istep)
-            loss = render_loss(kd_param, inv, p, target)
-            loss.backward()
-            opt.step()
-            with torch.no_grad():
-                kd_param.clamp_(1e-3, 1.0)
-            return loss
-
-        for it in range(3):
-            inv_iter(1000 + it)
+        ip = ipt.default_params(width=500, height=500, spp=64, max_depth=0, row_begin=ib, row_end=ie, row_step=istep)
+        opt = inverse_optimizer(inv, ip, target, lr=0.02)
+        opt.set_kd(np.full((inv.nT, 3), 0.5, np.float32))
+        opt.step(1000, 5)
+        opt.state()
         barrier()
-        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 20
-        i0.record()
-        for it in range(iters):
-            last = inv_iter(it)
-        i1.record()
-        barrier()
-        ims = max_over_ranks(i0.elapsed_time(i1))
-        extra["inverse_scene0_500x500_64spp"] = {"iters_per_s": iters / (ims * 1e-3), "ms_per_iter": ims / iters, "loss_after": float(last.detach())}
+        iters = 100
+        t0 = time.perf_counter()
+        opt.step(0, iters)
+        loss_after, _, _ = opt.state()
+        i_dt = max_over_ranks(time.perf_counter() - t0)
+        ik = inv.scene.kernel_times_ms(1)            # forward + loss + adjoint chains of the last iteration, one CUDA-event interval
+        ic = inv.scene.last_counters()               # rays of the last adjoint pass (the forward pass traces the same paths)
+        i_rays = 2 * (ic["ext_rays"] + ic["shadow_rays"])
+        inv_extra = {"iters_per_s": iters / i_dt, "ms_per_iter": 1e3 * i_dt / iters, "loss_after": loss_after, "impl": "iptInverseStep (in-library loop)",
+                     "timing": "wall clock around %d iterations enqueued by one call + the final state read-back, max over ranks" % iters,
+                     "kernel_ms": float(ik[0]) if len(ik) else None}
+        if len(ik):
+            inv_extra["roofline"] = fp32_roofline(i_rays, inv.nT, float(ik[0]))
+            inv_extra["roofline"]["note"] = "forward + adjoint passes of one iteration on this rank (row chunks on overlapping streams); the adjoint replays the forward paths (same rays)"
+        opt.close()
+        if world == 1:
+            # the Python loop this replaces (render_loss + torch.optim.Adam), for comparison
+            kd_param = torch.full((inv.nT, 3), 0.5, device=dev, requires_grad=True)
+            adam = torch.optim.Adam([kd_param], lr=0.02)
+
+            def inv_iter(it):
+                adam.zero_grad(set_to_none=True)
+                loss = render_loss(kd_param, inv, ipt.default_params(width=500, height=500, spp=64, max_depth=0, seed=it), target)
+                loss.backward()
+                adam.step()
+                with torch.no_grad():
+                    kd_param.clamp_(1e-3, 1.0)
+            for it in range(3):
+                inv_iter(1000 + it)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for it in range(20):
+                inv_iter(it)
+            torch.cuda.synchronize()
+            inv_extra["python_loop_iters_per_s"] = 20 / (time.perf_counter() - t0)
+        extra["inverse_scene0_500x500_64spp"] = inv_extra
+
         # ---- scene-sharded batch inverse (BASELINE config 4): every rank fits its own scene (scenes/<rank>.txt) against
-        #      its own target (forward render, 100 spp, seed = scene id); no collective; aggregate iterations/s
+        #      its own target (forward render, 100 spp, seed = scene id); no exchange; aggregate iterations/s
         mine = TorchScene(parse_scene_file(os.path.join(ASSETS, "scenes", "%d.txt" % rank)), asset_root=ASSETS, device=local)
         tgt8 = torch.empty((500, 500, 3), dtype=torch.uint8, device=dev)
         mine.render(ipt.default_params(width=500, height=500, spp=100, seed=rank), out_u8=tgt8)
-        kd2 = torch.full((mine.nT, 3), 0.5, device=dev, requires_grad=True)
-        opt2 = torch.optim.Adam([kd2], lr=0.02)
-
-        def batch_iter(it):
-            opt2.zero_grad(set_to_none=True)
-            loss = render_loss(kd2, mine, ipt.default_params(width=500, height=500, spp=64, max_depth=0, seed=it), tgt8, reduce=False)
-            loss.backward()
-            opt2.step()
-            with torch.no_grad():
-                kd2.clamp_(1e-3, 1.0)
-            return loss
-
-        for it in range(3):
-            batch_iter(1000 + it)
+        torch.cuda.synchronize()
+        bopt = native.InverseOptimizer(mine.scene, ipt.default_params(width=500, height=500, spp=64, max_depth=0), tgt8.data_ptr(), lr=0.02)
+        bopt.set_kd(np.full((mine.nT, 3), 0.5, np.float32))
+        bopt.step(1000, 3)
+        bopt.state()
         barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for it in range(iters):
-            lastb = batch_iter(it)
-        b1.record()
-        barrier()
-        bms = max_over_ranks(b0.elapsed_time(b1))
-        extra["inverse_batch_scene_sharded_500x500_64spp"] = {"iters_per_s": world * iters / (bms * 1e-3), "scenes_in_flight": world,
-                                                               "ms_per_iter_per_gpu": bms / iters, "loss_after_rank0": float(lastb.detach())}
+        t0 = time.perf_counter()
+        bopt.step(0, 40)
+        lossb, _, _ = bopt.state()
+        b_dt = max_over_ranks(time.perf_counter() - t0)
+        extra["inverse_batch_scene_sharded_500x500_64spp"] = {"iters_per_s": world * 40 / b_dt, "scenes_in_flight": world, "ms_per_iter_per_gpu": 1e3 * b_dt / 40,
+                                                               "loss_after_rank0": lossb}
+        bopt.close()
         mine.close()
         inv.close()
-        # ---- BVH scenes (BASELINE config 5 at bench scale): room + 327 680-triangle sphere, wavefront integrator;
-        #      rank 0 of a single-GPU run only (the stress tool runs the 5.2 M-triangle version)
-        if world == 1:
-            import importlib.util
-            import tempfile
-            spec = importlib.util.spec_from_file_location("stress_config5", os.path.join(ROOT, "tools", "stress_config5.py"))
-            stress = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(stress)
-            sobjs, sphere_tris = stress.stress_scene_objects(4, tempfile.mkdtemp(prefix="ipt_bench_"))
-            bs = TorchScene(sobjs, asset_root=ASSETS, device=local)
-            bout = torch.empty((1024, 1024, 3), dtype=torch.float32, device=dev)
-            bp = lambda s_: ipt.default_params(width=1024, height=1024, spp=4, max_depth=8, seed=s_)
-            for i in range(2):
-                bs.render(bp(50 + i), out=bout, counters=counters)
-            total.zero_()
-            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            v0.record()
-            for i in range(5):
-                bs.render(bp(i), out=bout, counters=counters)
-                total.add_(counters)
-            v1.record()
-            torch.cuda.synchronize()
-            vms = v0.elapsed_time(v1)
-            vc = [int(x) for x in total.tolist()]
-            extra["bvh_room_sphere_1024x1024_4spp_depth8"] = {"triangles": int(bs.nT), "integrator": "wavefront", "mrays_per_s": (vc[1] + vc[2]) / (vms * 1e-3) / 1e6,
-                                                              "mpaths_per_s": vc[0] / (vms * 1e-3) / 1e6, "ms_per_frame": vms / 5}
-            bs.close()
+
+        # ---- BASELINE config 5 (stress): room + shapes/sphere.obj subdivided to 5 242 880 triangles, 1024 x 1024, 16 spp,
+        #      depth 8, wavefront integrator; incoherent closest hit with its HBM roofline (algorithmic bytes per ray
+        #      from the instrumented traversal, iptTraceRaysStatsDevice).  Rank 0 of a single-GPU run only.
+        if world == 1 and not args.no_stress:
+            extra["config5_room_sphere_5p2M_triangles"] = config5_extra(args, ipt, native, torch, np, dev, peaks, peak_kind)
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import oracle as O
+        kind = O.use_native_build()
         osc = O.OracleScene(CORNELL, ASSETS)
         threads = O.hardware_threads() or 1
         ccnt, cdt, band = run_cpu_sample(O, osc, 0, args.cpu_rows, threads)
         cpu = {"value": (ccnt["ext_rays"] + ccnt["shadow_rays"]) / cdt / 1e6, "unit": "Mrays/s", "cores": threads, "kind": "port",
-               "sample": "rows [%d,%d) of the %dx%d image at %d spp (%d paths, %.1f s), CPU oracle on %d host threads" % (
-                   band[0], band[1], WORKLOAD["width"], WORKLOAD["height"], WORKLOAD["spp"], ccnt["paths"], cdt, threads)}
+               "sample": "rows [%d,%d) of the %dx%d image at %d spp (%d paths, %.1f s), CPU oracle on %d host threads, built %s" % (
+                   band[0], band[1], WORKLOAD["width"], WORKLOAD["height"], WORKLOAD["spp"], ccnt["paths"], cdt, threads, kind)}
+        if not args.no_extras:
+            # the metric point on the CPU: the full 512 x 512 x 64 spp frame
+            r, pth, dt, _ = cpu_render_rate(O, osc, threads, width=512, height=512, spp=64, max_depth=0)
+            extra["metric_point_cornell_512x512_64spp_unbounded"]["cpu_baseline"] = {
+                "value": r, "unit": "Mrays/s", "mpaths_per_s": pth, "cores": threads, "kind": "port",
+                "sample": "the whole 512x512x64 spp frame (%.1f s), CPU oracle on %d host threads, built %s" % (dt, threads, kind)}
+            # BASELINE config 1 / BASELINE.md section 5: 256 x 256, 16 spp, depth 5, one thread and all threads, best of 3
+            c1 = {}
+            for name, th in (("one_thread", 1), ("all_threads", threads)):
+                r, pth, dt, _ = cpu_render_rate(O, osc, th, reps=3, width=256, height=256, spp=16, max_depth=5)
+                c1[name] = {"mrays_per_s": r, "mpaths_per_s": pth, "seconds": dt, "threads": th}
+            c1["build"] = kind
+            extra["cpu_config1_cornell_256x256_16spp_depth5"] = c1
 
     launches = native.lib().iptKernelLaunchCount() - launches0
     if rank == 0:
@@ -413,11 +471,10 @@ def b200_arm(args):
                 "config": {"workload": w["name"], "scene": "CornellBox-Empty-CO (18 triangles, 2 emissive), scene replicated",
                            "sharding": "interleaved pixel rows (rank, rank+N, ...), all-gather of the float image" if world > 1 else "single GPU",
                            "rng": "Philox4x32-10 keyed (pixel, sample, bounce), seed = step index",
-                           "l2": "flushed between iterations by a 256 MiB device write (inside the timed region)"},
-                "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-                             "frac": achieved_tflops / peak_tflops, "traffic": traffic,
-                             "peak_source": "%s: %d SMs x 128 lanes x 2 x sm_max_mhz %.0f" % (peak_kind, sm_count, peaks["sm_max_mhz"]),
-                             "algorithmic": "%d FLOP per ray-triangle test x %d triangles per ray" % (FLOP_PER_TEST, nT)},
+                           "l2": "flushed between iterations by a 256 MiB device write (inside the timed region)",
+                           "metric_point": "BASELINE.json quotes its metric on CornellBox 512x512x64 spp: extra.metric_point_cornell_512x512_64spp_unbounded "
+                                           "carries that point with its own roofline, e2e and cpu_baseline"},
+                "roofline": roofline,
                 "cpu_baseline": cpu,
                 "e2e": {"value": e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(nT * 3 * 4),
                         "d2h_bytes_per_step": int(rows * w["width"] * 3 * 4 + 24), "steps": e2e_steps},
@@ -426,6 +483,74 @@ def b200_arm(args):
     ts.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def config5_extra(args, ipt, native, torch, np, dev, peaks, peak_kind):
+    import ctypes as C
+    import importlib.util
+    import tempfile
+    spec = importlib.util.spec_from_file_location("stress_config5", os.path.join(ROOT, "tools", "stress_config5.py"))
+    stress = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(stress)
+    t0 = time.perf_counter()
+    sobjs, sphere_tris = stress.stress_scene_objects(6, tempfile.mkdtemp(prefix="ipt_bench_"))
+    t_gen = time.perf_counter() - t0
+    L = native.lib()
+    k0 = L.iptKernelLaunchCount()
+    t0 = time.perf_counter()
+    sc = ipt.Scene(sobjs)
+    t_load = time.perf_counter() - t0
+    tab = sc.triangle_table()
+    boxes = np.concatenate([tab["verts"].min(1), tab["verts"].max(1)], 1)
+    t0 = time.perf_counter()
+    nb, ni, perm = native.build_bvh(boxes, tab["center"], builder=2)
+    t_bvh = time.perf_counter() - t0
+    out = {"triangles": int(sc.nT), "bvh_nodes": int(sc.n_nodes), "large_triangle_set": int(sc.n_large), "generate_obj_s": t_gen,
+           "load_scene_s": t_load, "bvh_build_s": t_bvh,
+           "bvh_build_note": "iptBuildBVH, CUDA builder, %d primitives, including the host<->device copies" % boxes.shape[0]}
+    # path tracing through the wavefront integrator
+    p = lambda s_: ipt.default_params(width=1024, height=1024, spp=16, max_depth=8, seed=s_)
+    sc.render(p(50))
+    best = None
+    for i in range(3):
+        _, cnt = sc.render(p(i))
+        ms = float(sc.kernel_times_ms(1)[0])
+        if best is None or ms < best[0]:
+            best = (ms, cnt)
+    out["path_tracing_1024x1024_16spp_depth8"] = {"integrator": "wavefront", "ms_per_frame": best[0], "mrays_per_s": (best[1]["ext_rays"] + best[1]["shadow_rays"]) / best[0] / 1e3,
+                                                  "mpaths_per_s": best[1]["paths"] / best[0] / 1e3}
+    # incoherent closest hit: random origins inside the room, random directions
+    rng = np.random.RandomState(0)
+    n = 8_000_000
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    o = rng.uniform([-1.9, -1.9, 1.1], [1.9, 1.9, 4.9], (n, 3))
+    rd = torch.from_numpy(np.concatenate([o, d], 1).astype(np.float32)).to(dev)
+    tri = torch.empty(n, dtype=torch.int32, device=dev); tt = torch.empty(n, dtype=torch.float32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    stats = torch.zeros(2, dtype=torch.int64, device=dev)
+    L.iptTraceRaysStatsDevice(sc.h, C.c_void_p(rd.data_ptr()), n, C.c_void_p(tri.data_ptr()), C.c_void_p(tt.data_ptr()), C.c_void_p(stats.data_ptr()), st)
+    torch.cuda.synchronize()
+    boxes_per_ray, tris_per_ray = float(stats[0]) / n, float(stats[1]) / n
+    bytes_per_ray = boxes_per_ray * 32 + tris_per_ray * 64
+    best_ms = None
+    for rep in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.iptTraceRaysDevice(sc.h, C.c_void_p(rd.data_ptr()), n, C.c_void_p(tri.data_ptr()), C.c_void_p(tt.data_ptr()), st)
+        e1.record(); torch.cuda.synchronize()
+        m = e0.elapsed_time(e1)
+        best_ms = m if best_ms is None or m < best_ms else best_ms
+    ach = n * bytes_per_ray / (best_ms * 1e-3) / 1e9
+    out["incoherent_closest_hit"] = {"rays": n, "ms": best_ms, "mrays_per_s": n / best_ms / 1e3, "hit_rate": float((tri >= 0).float().mean()),
+                                     "child_boxes_per_ray": boxes_per_ray, "leaf_triangles_per_ray": tris_per_ray,
+                                     "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                                                  "peak_source": "%s HBM copy bandwidth (MEASURED_PEAKS.json)" % peak_kind,
+                                                  "l2_resident_copy_gbs": native.measure_copy_gbps(32 << 20, 20),
+                                                  "algorithmic": "%.1f child boxes x 32 B + %.2f leaf triangles x 64 B = %.0f bytes per ray (iptTraceRaysStatsDevice)" % (
+                                                      boxes_per_ray, tris_per_ray, bytes_per_ray)}}
+    out["kernel_launches"] = int(L.iptKernelLaunchCount() - k0)
+    sc.close()
+    return out
 
 
 def main():
@@ -437,6 +562,7 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=128, help="rows of the 1024-wide image rendered per CPU sample (128 rows = 134 M paths, about 13 s on 16 host threads)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-stress", action="store_true", help="skip the 5.2 M-triangle config-5 extra (about 40 s)")
     ap.add_argument("--small", action="store_true", help="developer smoke run (not a bench number)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and not args.small:

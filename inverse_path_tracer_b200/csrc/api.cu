@@ -370,20 +370,87 @@ int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan) {
   return 0;
 }
 
+// ---- chunked launches ------------------------------------------------------------------------------------------
+// A persistent launch ends in a tail: the work queue is empty and the warps run on for as long as their longest path
+// (path lengths are geometric; ~90 bounces among 10^5 lanes), most lanes idle.  For a 1024^2 x 1024 spp frame that is
+// nothing; for one rank's share of a 500^2 x 64 spp inverse iteration (20 paths per lane) it was a third of the kernel
+// (profiles/r02_inverse_overhead.txt).  Small launches are therefore split into up to kMaxChunks row blocks issued on
+// separate internal streams: a chunk's blocks take over the SM slots the previous chunk's blocks give up as they run
+// dry, so only the last chunk's tail is exposed.  Chunks share the handle's buffers at disjoint offsets.
+int pick_chunks(const SceneHandle* h, const Plan& plan) {
+  const char* env = getenv("IPT_CHUNKS");   // developer A/B
+  int k = h->chunks;
+  if (env && *env) k = atoi(env);
+  if (k <= 0) {
+    const long long lanes = (long long)h->sm_count * 5 * paths_block_threads();
+    const long long per_lane = (long long)plan.rp.n_pix * plan.rp.spp / std::max<long long>(lanes, 1);
+    k = per_lane >= 512 ? 1 : (per_lane >= 128 ? 2 : 4);
+  }
+  return std::max(1, std::min(std::min(k, SceneHandle::kMaxChunks), plan.rows));
+}
+
+Fork::Fork(SceneHandle* h_, cudaStream_t st_, int k_) : h(h_), st(st_), k(k_) {}
+cudaError_t Fork::begin() {
+  if (k <= 1) return cudaSuccess;
+  cudaError_t e = cudaEventRecord(h->ev_fork, st);
+  for (int c = 0; c < k && e == cudaSuccess; c++) e = cudaStreamWaitEvent(h->cstream[c], h->ev_fork, 0);
+  return e;
+}
+cudaError_t Fork::end() {
+  if (k <= 1) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  for (int c = 0; c < k && e == cudaSuccess; c++) {
+    e = cudaEventRecord(h->ev_join[c], h->cstream[c]);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, h->ev_join[c], 0);
+  }
+  return e;
+}
+
+// rows [lr0, lr1) of the shard (shard-local row indices) that chunk c of k covers, and the render descriptor of that block
+void chunk_render(const Plan& plan, int c, int k, DevRender* rp_c, int* lr0, int* lr1) {
+  *lr0 = (int)((long long)plan.rows * c / k);
+  *lr1 = (int)((long long)plan.rows * (c + 1) / k);
+  *rp_c = plan.rp;
+  rp_c->row_begin = plan.rp.row_begin + *lr0 * plan.rp.row_step;
+  rp_c->n_pix = (*lr1 - *lr0) * plan.rp.width;
+}
+
+int prepare_forward(SceneHandle* h, const Plan& plan) {
+  IPT_CUDA(h->partial.reserve((size_t)plan.rp.n_pix * plan.rp.groups * 3 * sizeof(float)));
+  IPT_CUDA(h->counters.reserve(16 * sizeof(unsigned long long)));
+  return 0;
+}
+
+// forward pass of chunk c into its block of h->partial, on `st_c`.  counters[0..2] are shared by the chunks (atomics)
+// and must have been zeroed by the caller; the chunk's work counter is ctr[4 + c].
+int forward_chunk(SceneHandle* h, const Plan& plan, const DevScene& sc, int c, int k, unsigned long long* counters, cudaStream_t st_c) {
+  DevRender rp;
+  int lr0, lr1;
+  chunk_render(plan, c, k, &rp, &lr0, &lr1);
+  if (lr1 <= lr0) return 0;
+  unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
+  DevOut out;
+  memset(&out, 0, sizeof(out));
+  out.work_counter = reinterpret_cast<unsigned*>(ctr + 4 + c);
+  out.counters = counters;
+  out.partial = (float*)h->partial.ptr + (size_t)lr0 * rp.width * rp.groups * 3;
+  const size_t smem = paths_smem_bytes(sc, 0);
+  const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, sc, smem);
+  IPT_CUDA(launch_paths(MODE_RENDER_ID, sc, rp, out, grid, smem, st_c));
+  g_launches += 1;
+  return 0;
+}
+
 int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev,
                    cudaStream_t st, bool resolve) {
   const DevScene sc = h->dev();
   const DevRender& rp = plan.rp;
-  IPT_CUDA(h->partial.reserve((size_t)rp.n_pix * rp.groups * 3 * sizeof(float)));
-  IPT_CUDA(h->counters.reserve(8 * sizeof(unsigned long long)));
+  if (prepare_forward(h, plan) != 0) return -1;
   unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
-  IPT_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
+  IPT_CUDA(cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned long long), st));
   if (counters_dev) IPT_CUDA(cudaMemsetAsync(counters_dev, 0, 3 * sizeof(unsigned long long), st));
-  DevOut out;
-  memset(&out, 0, sizeof(out));
-  out.work_counter = reinterpret_cast<unsigned*>(ctr + 4);
-  out.counters = counters_dev ? counters_dev : ctr;
-  out.partial = (float*)h->partial.ptr;
+  unsigned long long* counters = counters_dev ? counters_dev : ctr;
+  float* partial = (float*)h->partial.ptr;
   if ((sc.use_bvh && h->integrator != 1) || (!sc.use_bvh && h->integrator == 2)) {
     // large scenes: wavefront (wavefront.cu); batches of at most `cap` paths
     const long long total = (long long)rp.n_pix * rp.spp;
@@ -393,72 +460,100 @@ int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned ch
     const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
     IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
     unsigned long long launches = 0;
-    IPT_CUDA(launch_wavefront(sc, rp, h->wavefront.ptr, cap, out.partial, out.counters, h->sm_count, h->host_live, &launches, st));
+    IPT_CUDA(launch_wavefront(sc, rp, h->wavefront.ptr, cap, partial, counters, h->sm_count, h->host_live, &launches, st));
     IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
     h->ev_count++;
     g_launches += launches;
   } else {
-    const size_t smem = paths_smem_bytes(sc, 0);
-    const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, sc, smem);
+    const int k = pick_chunks(h, plan);
     const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
     IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
-    IPT_CUDA(launch_paths(MODE_RENDER_ID, sc, rp, out, grid, smem, st));
+    Fork f(h, st, k);
+    IPT_CUDA(f.begin());
+    for (int c = 0; c < k; c++)
+      if (forward_chunk(h, plan, sc, c, k, counters, f.stream(c)) != 0) return -1;
+    IPT_CUDA(f.end());
     IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
     h->ev_count++;
-    g_launches += 1;
   }
   if (!resolve) return 0;
-  IPT_CUDA(launch_resolve(out.partial, rp.n_pix, rp.groups, img_dev, img8_dev, st));
+  IPT_CUDA(launch_resolve(partial, rp.n_pix, rp.groups, img_dev, img8_dev, st));
+  g_launches += 1;
+  return 0;
+}
+
+// gradient tiles: one [3 nT] float tile per block in global memory, updated with fire-and-forget float reductions
+// (shared-memory float atomics are compare-and-swap loops on this architecture); scenes whose tiles would be too
+// large fall back to double atomics on the result itself
+int prepare_grad(SceneHandle* h, const Plan& plan, int k, GradLaunch* g) {
+  const DevScene sc = h->dev();
+  const int nT = sc.nT;
+  const char* acc_env = getenv("IPT_GRAD_ACC");   // developer A/B: 0 = global double, 1 = shared tile, 2 = global tile
+  g->smem = paths_smem_bytes(sc, 0);
+  g->acc_mode = (3 * (size_t)nT <= 65536) ? 2 : 0;
+  if (acc_env && *acc_env) g->acc_mode = atoi(acc_env);
+  if (g->acc_mode == 1) g->smem = paths_smem_bytes(sc, 3 * nT);
+  g->grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, sc, g->smem);
+  g->vdepth = plan.rp.max_depth;
+  IPT_CUDA(h->counters.reserve(16 * sizeof(unsigned long long)));
+  if (g->acc_mode) IPT_CUDA(h->block_acc.reserve((size_t)k * g->grid * 3 * nT * sizeof(float)));
+  // adjoint vertex stacks: two halves of max_depth 32-byte vertices per resident thread (no initialisation needed:
+  // a sweep only reads what its own path wrote)
+  g->vstack_bytes = (size_t)g->grid * paths_block_threads() * 2 * (size_t)g->vdepth * 32;
+  IPT_CUDA(h->vstacks.reserve((size_t)k * g->vstack_bytes));
+  return 0;
+}
+
+// path adjoint of chunk c on `st_c`; h->dldpx holds dLoss/dL of the whole shard, ctr[0..2] were zeroed by the caller
+int grad_chunk(SceneHandle* h, const Plan& plan, const DevScene& sc, const GradLaunch& g, int c, int k, const unsigned char* target_dev,
+               double* lossgrad_dev, cudaStream_t st_c) {
+  DevRender rp;
+  int lr0, lr1;
+  chunk_render(plan, c, k, &rp, &lr0, &lr1);
+  if (lr1 <= lr0) return 0;
+  const int nT = sc.nT;
+  unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
+  DevOut out;
+  memset(&out, 0, sizeof(out));
+  out.work_counter = reinterpret_cast<unsigned*>(ctr + 4 + c);
+  out.counters = ctr;
+  out.target = target_dev;
+  out.dldpx = (const float*)h->dldpx.ptr + (size_t)lr0 * rp.width * 3;
+  out.acc_stride = 3 * nT;
+  out.acc_in_smem = g.acc_mode;
+  if (g.acc_mode) {
+    out.block_acc = (float*)h->block_acc.ptr + (size_t)c * g.grid * 3 * nT;
+    if (g.acc_mode == 2) IPT_CUDA(cudaMemsetAsync(out.block_acc, 0, (size_t)g.grid * 3 * nT * sizeof(float), st_c));
+  } else {
+    out.global_acc = lossgrad_dev + 1;
+  }
+  out.vdepth = g.vdepth;
+  out.vstacks = (float4*)((char*)h->vstacks.ptr + (size_t)c * g.vstack_bytes);
+  IPT_CUDA(launch_paths(MODE_GRAD_ID, sc, rp, out, g.grid, g.smem, st_c));
   g_launches += 1;
   return 0;
 }
 
 int launch_grad_pass(SceneHandle* h, const Plan& plan, const unsigned char* target_dev, double* lossgrad_dev, cudaStream_t st) {
   const DevScene sc = h->dev();
-  const DevRender& rp = plan.rp;
   const int nT = sc.nT;
   if (nT == 0) return 0;
-  IPT_CUDA(h->counters.reserve(8 * sizeof(unsigned long long)));
+  const int k = pick_chunks(h, plan);
+  GradLaunch g;
+  if (prepare_grad(h, plan, k, &g) != 0) return -1;
   unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
-  IPT_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
-  DevOut out;
-  memset(&out, 0, sizeof(out));
-  out.work_counter = reinterpret_cast<unsigned*>(ctr + 4);
-  out.counters = ctr;
-  out.target = target_dev;
-  out.dldpx = (const float*)h->dldpx.ptr;
-  out.acc_stride = 3 * nT;
-  // gradient tiles: one [3 nT] float tile per block in global memory, updated with fire-and-forget float
-  // reductions (shared-memory float atomics are compare-and-swap loops on this architecture); scenes whose
-  // tiles would be too large fall back to double atomics on the result itself
-  const char* acc_env = getenv("IPT_GRAD_ACC");   // developer A/B: 0 = global double, 1 = shared tile, 2 = global tile
-  size_t smem = paths_smem_bytes(sc, 0);
-  out.acc_in_smem = (3 * (size_t)nT <= 65536) ? 2 : 0;
-  if (acc_env && *acc_env) out.acc_in_smem = atoi(acc_env);
-  if (out.acc_in_smem == 1) smem = paths_smem_bytes(sc, 3 * nT);
-  const int grid = h->sm_count * paths_blocks_per_sm(MODE_GRAD_ID, sc, smem);
-  if (out.acc_in_smem) {
-    IPT_CUDA(h->block_acc.reserve((size_t)grid * 3 * nT * sizeof(float)));
-    out.block_acc = (float*)h->block_acc.ptr;
-    if (out.acc_in_smem == 2) IPT_CUDA(cudaMemsetAsync(out.block_acc, 0, (size_t)grid * 3 * nT * sizeof(float), st));
-  } else {
-    out.global_acc = lossgrad_dev + 1;
-  }
-  // adjoint vertex stacks: two halves of max_depth 32-byte vertices per resident thread (no initialisation needed:
-  // a sweep only reads what its own path wrote)
-  out.vdepth = rp.max_depth;
-  IPT_CUDA(h->vstacks.reserve((size_t)grid * paths_block_threads() * 2 * (size_t)out.vdepth * 32));
-  out.vstacks = (float4*)h->vstacks.ptr;
-  {
-    const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
-    IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
-    IPT_CUDA(launch_paths(MODE_GRAD_ID, sc, rp, out, grid, smem, st));
-    IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
-    h->ev_count++;
-  }
-  g_launches += 1;
-  if (out.acc_in_smem) {
-    IPT_CUDA(launch_reduce_blocks(out.block_acc, grid, 3 * nT, lossgrad_dev + 1, 0, 0, st));
+  IPT_CUDA(cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned long long), st));
+  const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
+  IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
+  Fork f(h, st, k);
+  IPT_CUDA(f.begin());
+  for (int c = 0; c < k; c++)
+    if (grad_chunk(h, plan, sc, g, c, k, target_dev, lossgrad_dev, f.stream(c)) != 0) return -1;
+  IPT_CUDA(f.end());
+  IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
+  h->ev_count++;
+  if (g.acc_mode) {
+    IPT_CUDA(launch_reduce_blocks((const float*)h->block_acc.ptr, k * g.grid, 3 * nT, lossgrad_dev + 1, 0, 0, st));
     g_launches += 1;
   }
   return 0;
@@ -589,6 +684,11 @@ int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mt
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->busy, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  for (int i = 0; i < SceneHandle::kMaxChunks && e == cudaSuccess; i++) {
+    e = cudaStreamCreateWithFlags(&h->cstream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+  }
   for (int i = 0; i < SceneHandle::kEventRing && e == cudaSuccess; i++) {
     e = cudaEventCreate(&h->ev_start[i]);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev_stop[i]);
@@ -829,9 +929,9 @@ int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsign
   const int acc_floats = n_edges * kGraphAccPerEdge;
   IPT_CUDA(cudaMemsetAsync(raw_dev, 0, (size_t)n_edges * 16 * sizeof(double), st));
   if (nT == 0) return 0;
-  IPT_CUDA(h->counters.reserve(8 * sizeof(unsigned long long)));
+  IPT_CUDA(h->counters.reserve(16 * sizeof(unsigned long long)));
   unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
-  IPT_CUDA(cudaMemsetAsync(ctr, 0, 8 * sizeof(unsigned long long), st));
+  IPT_CUDA(cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned long long), st));
   IPT_CUDA(h->acc.reserve((size_t)acc_floats * sizeof(double)));
   IPT_CUDA(cudaMemsetAsync(h->acc.ptr, 0, (size_t)acc_floats * sizeof(double), st));
   DevOut out;

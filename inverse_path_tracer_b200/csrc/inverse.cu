@@ -222,16 +222,44 @@ static int enqueue_step(InverseHandle* o, unsigned long long seed) {
     }
   }
   const DevRender& rp = plan.rp;
+  const DevScene sc = h->dev();
   const size_t n3 = (size_t)rp.n_pix * 3;
+  const int k = pick_chunks(h, plan);
+  GradLaunch g;
   IPT_CUDA(h->dldpx.reserve(n3 * sizeof(float)));
-  if (launch_forward(h, plan, nullptr, nullptr, nullptr, st, /*resolve=*/false) != 0) return -1;
+  if (prepare_forward(h, plan) != 0 || prepare_grad(h, plan, k, &g) != 0) return -1;
+  unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
   IPT_CUDA(cudaMemsetAsync(o->st.lossgrad, 0, (size_t)o->n * sizeof(double), st));
   const double inv_n = 1.0 / (3.0 * (double)rp.width * (double)rp.height);
-  k_resolve_loss<<<(rp.n_pix + 255) / 256, 256, 0, st>>>((const float*)h->partial.ptr, rp.n_pix, rp.groups, o->target_dev, rp.row_begin, rp.row_step, rp.width,
-                                                         inv_n, 1.0f / (float)rp.spp, nullptr, (float*)h->dldpx.ptr, o->st.lossgrad);
-  IPT_CUDA(cudaGetLastError());
-  g_launches += 1;
-  if (launch_grad_pass(h, plan, o->target_dev, o->st.lossgrad, st) != 0) return -1;
+  // one chain per chunk of rows -- forward, toneMap + loss, adjoint -- on its own stream: the adjoint of the first rows
+  // fills the SMs that the forward pass of the last rows leaves idle in its tail (api.cu, "chunked launches")
+  Fork f(h, st, k);
+  IPT_CUDA(cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned long long), st));
+  const int slot = (int)(h->ev_count % SceneHandle::kEventRing);   // iptPathKernelTimes: forward + loss + adjoint of the iteration as one interval
+  IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
+  IPT_CUDA(f.begin());
+  for (int c = 0; c < k; c++) {
+    cudaStream_t sc_st = f.stream(c);
+    DevRender rc;
+    int lr0, lr1;
+    chunk_render(plan, c, k, &rc, &lr0, &lr1);
+    if (lr1 <= lr0) continue;
+    if (forward_chunk(h, plan, sc, c, k, ctr + 8, sc_st) != 0) return -1;   // ray counters of the forward pass go to ctr[8..10], the adjoint's to ctr[0..2]
+    const size_t p0 = (size_t)lr0 * rc.width;
+    k_resolve_loss<<<(rc.n_pix + 255) / 256, 256, 0, sc_st>>>((const float*)h->partial.ptr + p0 * rc.groups * 3, rc.n_pix, rc.groups, o->target_dev, rc.row_begin,
+                                                              rc.row_step, rc.width, inv_n, 1.0f / (float)rc.spp, nullptr, (float*)h->dldpx.ptr + p0 * 3, o->st.lossgrad);
+    IPT_CUDA(cudaGetLastError());
+    g_launches += 1;
+    IPT_CUDA(cudaMemsetAsync(ctr + 4 + c, 0, sizeof(unsigned long long), sc_st));   // the chunk's work counter, reused by its adjoint launch
+    if (grad_chunk(h, plan, sc, g, c, k, o->target_dev, o->st.lossgrad, sc_st) != 0) return -1;
+  }
+  IPT_CUDA(f.end());
+  IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
+  h->ev_count++;
+  if (g.acc_mode && o->nT) {
+    IPT_CUDA(launch_reduce_blocks((const float*)h->block_acc.ptr, k * g.grid, 3 * o->nT, o->st.lossgrad + 1, 0, 0, st));
+    g_launches += 1;
+  }
   k_inverse_update<<<1, 256, 0, st>>>(o->st, o->peers, o->cfg.rank, o->cfg.world, o->nT, h->mat, o->cfg.lr, o->cfg.beta1, o->cfg.beta2, o->cfg.eps,
                                      o->cfg.kd_min, o->cfg.kd_max, kHistoryCap, (unsigned long long)(o->cfg.timeout_ms > 0 ? o->cfg.timeout_ms : 10000) * 1000000ull);
   IPT_CUDA(cudaGetLastError());

@@ -74,6 +74,11 @@ struct SceneHandle {
   // counter and the event ring are per handle), and calls enqueued on DIFFERENT streams are chained through `busy`
   // (recorded after each call, waited on by the next), so two calls in flight on one scene cannot share scratch.
   std::recursive_mutex mutex;
+  // chunked launches (api.cu): internal streams and fork / join events; `chunks` = 0 picks the count from the launch size
+  static constexpr int kMaxChunks = 4;
+  cudaStream_t cstream[kMaxChunks] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {};
+  int chunks = 0;
   cudaEvent_t busy = nullptr;
   bool busy_recorded = false;
   cudaStream_t busy_stream = nullptr;
@@ -94,6 +99,8 @@ struct SceneHandle {
     for (Scratch* s : all) s->release();
     if (host_live) cudaFreeHost(host_live);
     if (busy) cudaEventDestroy(busy);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (int i = 0; i < kMaxChunks; i++) { if (cstream[i]) { cudaStreamSynchronize(cstream[i]); cudaStreamDestroy(cstream[i]); } if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
     if (stream) cudaStreamDestroy(stream);
     for (int i = 0; i < kEventRing; i++) { if (ev_start[i]) cudaEventDestroy(ev_start[i]); if (ev_stop[i]) cudaEventDestroy(ev_stop[i]); }
   }
@@ -127,6 +134,28 @@ struct Plan {
   int rows;
 };
 int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan);
+
+// chunked launches (api.cu)
+struct Fork {   // `st` forks into k internal streams (begin) that join it again (end); k == 1: everything stays on st
+  SceneHandle* h;
+  cudaStream_t st;
+  int k;
+  Fork(SceneHandle* h, cudaStream_t st, int k);
+  cudaError_t begin();
+  cudaError_t end();
+  cudaStream_t stream(int c) const { return k <= 1 ? st : h->cstream[c]; }
+};
+struct GradLaunch {
+  size_t smem, vstack_bytes;
+  int grid, acc_mode, vdepth;
+};
+int pick_chunks(const SceneHandle* h, const Plan& plan);
+void chunk_render(const Plan& plan, int c, int k, DevRender* rp_c, int* lr0, int* lr1);
+int prepare_forward(SceneHandle* h, const Plan& plan);
+int forward_chunk(SceneHandle* h, const Plan& plan, const DevScene& sc, int c, int k, unsigned long long* counters, cudaStream_t st_c);
+int prepare_grad(SceneHandle* h, const Plan& plan, int k, GradLaunch* g);
+int grad_chunk(SceneHandle* h, const Plan& plan, const DevScene& sc, const GradLaunch& g, int c, int k, const unsigned char* target_dev,
+               double* lossgrad_dev, cudaStream_t st_c);
 // forward pass of the shard into h->partial (+ toneMap into img_dev / img8_dev unless resolve == false)
 int launch_forward(SceneHandle* h, const Plan& plan, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev, cudaStream_t st,
                    bool resolve = true);
