@@ -373,19 +373,16 @@ int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan) {
 // ---- chunked launches ------------------------------------------------------------------------------------------
 // A persistent launch ends in a tail: the work queue is empty and the warps run on for as long as their longest path
 // (path lengths are geometric; ~90 bounces among 10^5 lanes), most lanes idle.  For a 1024^2 x 1024 spp frame that is
-// nothing; for one rank's share of a 500^2 x 64 spp inverse iteration (20 paths per lane) it was a third of the kernel
-// (profiles/r02_inverse_overhead.txt).  Small launches are therefore split into up to kMaxChunks row blocks issued on
-// separate internal streams: a chunk's blocks take over the SM slots the previous chunk's blocks give up as they run
-// dry, so only the last chunk's tail is exposed.  Chunks share the handle's buffers at disjoint offsets.
+// nothing; for one rank's share of a 500^2 x 64 spp inverse iteration (20 paths per lane) it is a quarter of each kernel.
+// A launch can be split into row blocks issued on separate internal streams (iptSceneSetChunks / IPT_CHUNKS), so that a
+// chunk's blocks take over the SM slots the previous chunk's blocks give up.  MEASURED SLOWER and therefore off by
+// default (profiles/r02_chunked_launches.txt: inverse iteration of a 1/8 shard 1.98 / 2.25 / 2.81 ms with 1 / 2 / 4 chunks,
+// Cornell 512^2 x 64 spp 3.20 / 3.32 / 3.50 ms): a block frees its slot only when all four of its warps have run dry,
+// which in the tail is almost as late as the end of the launch, so the chunks serialise and each adds its own tail.
 int pick_chunks(const SceneHandle* h, const Plan& plan) {
   const char* env = getenv("IPT_CHUNKS");   // developer A/B
   int k = h->chunks;
   if (env && *env) k = atoi(env);
-  if (k <= 0) {
-    const long long lanes = (long long)h->sm_count * 5 * paths_block_threads();
-    const long long per_lane = (long long)plan.rp.n_pix * plan.rp.spp / std::max<long long>(lanes, 1);
-    k = per_lane >= 512 ? 1 : (per_lane >= 128 ? 2 : 4);
-  }
   return std::max(1, std::min(std::min(k, SceneHandle::kMaxChunks), plan.rows));
 }
 
@@ -569,6 +566,19 @@ static uint64_t legacy_seed() {
 
 using namespace ipt;
 
+// No C++ exception may cross the C ABI (callers are ctypes / C): entry points that allocate on the host run their body
+// through this guard, which turns std::bad_alloc and friends into the library's error state.
+template <class F>
+static int guarded(const char* what, F&& body) {
+  try {
+    return body();
+  } catch (const std::exception& e) {
+    return fail(std::string(what) + ": " + e.what());
+  } catch (...) {
+    return fail(std::string(what) + ": unknown C++ exception");
+  }
+}
+
 extern "C" {
 
 const char* iptGetLastError(void) { return g_error.c_str(); }
@@ -653,16 +663,18 @@ int iptSetBvhBuilder(int mode) {
   return 0;
 }
 
-int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mtl_fs, int n, void** scenePtr) {
+static int load_scene_impl(float** poss, float** oris, float** scls, char** obj_fs, char** mtl_fs, int n, void** scenePtr, SceneHandle** in_flight) {
   if (scenePtr) *scenePtr = nullptr;
   if (!scenePtr || n < 0 || (n > 0 && (!poss || !oris || !scls || !obj_fs || !mtl_fs))) { fail("loadScene: bad arguments"); return 0; }
   SceneHandle* h = new SceneHandle();
+  *in_flight = h;   // the caller disposes of it if an exception unwinds this function
   h->traversal_mode = g_traversal_mode; h->big_max = g_big_max; h->integrator = g_integrator; h->wf_slots = g_wf_slots;
   std::string err;
   if (!build_host_scene(poss, oris, scls, obj_fs, mtl_fs, n, g_asset_root, &h->host, &err)) {
     fprintf(stderr, "ipt_b200: loadScene failed: %s\n", err.c_str());
     fail(err);
     delete h;
+    *in_flight = nullptr;
     return 0;
   }
   int dev = g_device;
@@ -671,12 +683,14 @@ int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mt
     std::lock_guard<std::mutex> lk(g_registry_mutex);
     g_registry.insert(h);
     *scenePtr = h;
+    *in_flight = nullptr;
     return (int)h->host.tris.size();
   }
   if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) {
     fail("ipt_b200: no CUDA device available (this library has no CPU fallback)");
     fprintf(stderr, "%s\n", g_error.c_str());
     delete h;
+    *in_flight = nullptr;
     return 0;
   }
   h->device = dev;
@@ -697,12 +711,14 @@ int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mt
     fail(std::string("ipt_b200: CUDA initialisation failed (no CPU fallback): ") + cudaGetErrorString(e));
     fprintf(stderr, "%s\n", g_error.c_str());
     delete h;
+    *in_flight = nullptr;
     return 0;
   }
   if (upload_scene(h) != 0) {
     fprintf(stderr, "ipt_b200: scene upload failed: %s\n", g_error.c_str());
     h->destroy();
     delete h;
+    *in_flight = nullptr;
     return 0;
   }
   {
@@ -710,7 +726,23 @@ int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mt
     g_registry.insert(h);
   }
   *scenePtr = h;
+  *in_flight = nullptr;
   return (int)h->host.tris.size();
+}
+
+int loadScene(float** poss, float** oris, float** scls, char** obj_fs, char** mtl_fs, int n, void** scenePtr) {
+  SceneHandle* in_flight = nullptr;
+  try {
+    return load_scene_impl(poss, oris, scls, obj_fs, mtl_fs, n, scenePtr, &in_flight);
+  } catch (const std::exception& e) {   // e.g. std::bad_alloc on a huge OBJ: no exception may cross the C ABI
+    fail(std::string("loadScene: ") + e.what());
+  } catch (...) {
+    fail("loadScene: unknown C++ exception");
+  }
+  fprintf(stderr, "ipt_b200: %s\n", iptGetLastError());
+  if (in_flight) { in_flight->destroy(); delete in_flight; }
+  if (scenePtr) *scenePtr = nullptr;
+  return 0;
 }
 
 void freeScene(void* scenePtr) {
@@ -737,29 +769,35 @@ static void sync_host_kd(SceneHandle* h) {
 }
 
 void getMaterials(void* scenePtr, float* materials) {
-  SceneHandle* h = checked(scenePtr);
-  if (!h || !materials) return;
-  std::lock_guard<std::recursive_mutex> lk(h->mutex);
-  sync_host_kd(h);
-  for (size_t i = 0; i < h->host.tris.size(); i++)
-    for (int j = 0; j < 3; j++) materials[3 * i + j] = h->host.tris[i].mat.kd[j];
+  guarded("getMaterials", [&]() -> int {
+    SceneHandle* h = checked(scenePtr);
+    if (!h || !materials) return 0;
+    std::lock_guard<std::recursive_mutex> lk(h->mutex);
+    sync_host_kd(h);
+    for (size_t i = 0; i < h->host.tris.size(); i++)
+      for (int j = 0; j < 3; j++) materials[3 * i + j] = h->host.tris[i].mat.kd[j];
+    return 0;
+  });
 }
 
 void setMaterials(void* scenePtr, float* materials) {
-  SceneHandle* h = checked(scenePtr);
-  if (!h || !materials) return;
-  std::lock_guard<std::recursive_mutex> lk(h->mutex);
-  for (size_t i = 0; i < h->host.tris.size(); i++)
-    for (int j = 0; j < 3; j++) h->host.tris[i].mat.kd[j] = materials[3 * i + j];
-  if (h->host_only) return;
-  std::vector<float4> mat;
-  pack_materials(h->host, &mat);
-  // the legacy call is fully synchronous like the reference's (scene.h:154-162 writes managed memory between renders):
-  // wait for everything queued on the device, on whatever stream, before the table is replaced
-  cudaSetDevice(h->device);
-  cudaDeviceSynchronize();
-  if (!mat.empty()) cudaMemcpy(h->mat, mat.data(), mat.size() * sizeof(float4), cudaMemcpyHostToDevice);
-  h->kd_dirty = false;
+  guarded("setMaterials", [&]() -> int {
+    SceneHandle* h = checked(scenePtr);
+    if (!h || !materials) return 0;
+    std::lock_guard<std::recursive_mutex> lk(h->mutex);
+    for (size_t i = 0; i < h->host.tris.size(); i++)
+      for (int j = 0; j < 3; j++) h->host.tris[i].mat.kd[j] = materials[3 * i + j];
+    if (h->host_only) return 0;
+    std::vector<float4> mat;
+    pack_materials(h->host, &mat);
+    // the legacy call is fully synchronous like the reference's (scene.h:154-162 writes managed memory between renders):
+    // wait for everything queued on the device, on whatever stream, before the table is replaced
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (!mat.empty()) cudaMemcpy(h->mat, mat.data(), mat.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    h->kd_dirty = false;
+    return 0;
+  });
 }
 
 int iptSetMaterialsDevice(void* scene, const float* kd_dev, void* stream) {
@@ -787,25 +825,27 @@ int iptSceneInfo(void* scene, int* n_triangles, int* n_emissives, int* n_objects
 
 int iptGetTriangleTable(void* scene, float* verts, float* kd, float* ks, float* ke, float* ns, int* has_vn, float* normal,
                         float* center, float* area) {
-  SceneHandle* h = checked(scene);
-  if (!h) return -1;
-  std::lock_guard<std::recursive_mutex> lk(h->mutex);
-  sync_host_kd(h);
-  for (size_t i = 0; i < h->host.tris.size(); i++) {
-    const HostTriangle& t = h->host.tris[i];
-    for (int j = 0; j < 3; j++) {
-      if (verts) for (int k = 0; k < 3; k++) verts[9 * i + 3 * j + k] = t.v[j][k];
-      if (kd) kd[3 * i + j] = t.mat.kd[j];
-      if (ks) ks[3 * i + j] = t.mat.ks[j];
-      if (ke) ke[3 * i + j] = t.mat.ke[j];
-      if (normal) normal[3 * i + j] = t.n[j];
-      if (center) center[3 * i + j] = t.c[j];
+  return guarded("iptGetTriangleTable", [&]() -> int {
+    SceneHandle* h = checked(scene);
+    if (!h) return -1;
+    std::lock_guard<std::recursive_mutex> lk(h->mutex);
+    sync_host_kd(h);
+    for (size_t i = 0; i < h->host.tris.size(); i++) {
+      const HostTriangle& t = h->host.tris[i];
+      for (int j = 0; j < 3; j++) {
+        if (verts) for (int k = 0; k < 3; k++) verts[9 * i + 3 * j + k] = t.v[j][k];
+        if (kd) kd[3 * i + j] = t.mat.kd[j];
+        if (ks) ks[3 * i + j] = t.mat.ks[j];
+        if (ke) ke[3 * i + j] = t.mat.ke[j];
+        if (normal) normal[3 * i + j] = t.n[j];
+        if (center) center[3 * i + j] = t.c[j];
+      }
+      if (ns) ns[i] = t.mat.ns;
+      if (has_vn) has_vn[i] = t.has_vn ? 1 : 0;
+      if (area) area[i] = t.area;
     }
-    if (ns) ns[i] = t.mat.ns;
-    if (has_vn) has_vn[i] = t.has_vn ? 1 : 0;
-    if (area) area[i] = t.area;
-  }
-  return 0;
+    return 0;
+  });
 }
 
 int iptGetCamera(void* scene, float* m16) {
@@ -844,21 +884,23 @@ int iptTraceRaysStatsDevice(void* scene, const float* rays_dev, int n, int* tri_
 }
 
 int iptTraceRays(void* scene, const float* rays, int n, int* tri, float* t) {
-  SceneHandle* h = checked_device(scene);
-  if (!h) return -1;
-  if (n < 0 || (n > 0 && (!rays || !tri || !t))) return fail("iptTraceRays: bad arguments");
-  if (n == 0) return 0;
-  std::lock_guard<std::recursive_mutex> lk(h->mutex);
-  IPT_CUDA(cudaSetDevice(h->device));
-  IPT_CUDA(h->rays.reserve((size_t)n * 6 * sizeof(float)));
-  IPT_CUDA(h->hits_tri.reserve((size_t)n * sizeof(int)));
-  IPT_CUDA(h->hits_t.reserve((size_t)n * sizeof(float)));
-  IPT_CUDA(cudaMemcpyAsync(h->rays.ptr, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  if (iptTraceRaysDevice(scene, (const float*)h->rays.ptr, n, (int*)h->hits_tri.ptr, (float*)h->hits_t.ptr, h->stream) != 0) return -1;
-  IPT_CUDA(cudaMemcpyAsync(tri, h->hits_tri.ptr, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  IPT_CUDA(cudaMemcpyAsync(t, h->hits_t.ptr, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  IPT_CUDA(cudaStreamSynchronize(h->stream));
-  return 0;
+  return guarded("iptTraceRays", [&]() -> int {
+    SceneHandle* h = checked_device(scene);
+    if (!h) return -1;
+    if (n < 0 || (n > 0 && (!rays || !tri || !t))) return fail("iptTraceRays: bad arguments");
+    if (n == 0) return 0;
+    std::lock_guard<std::recursive_mutex> lk(h->mutex);
+    IPT_CUDA(cudaSetDevice(h->device));
+    IPT_CUDA(h->rays.reserve((size_t)n * 6 * sizeof(float)));
+    IPT_CUDA(h->hits_tri.reserve((size_t)n * sizeof(int)));
+    IPT_CUDA(h->hits_t.reserve((size_t)n * sizeof(float)));
+    IPT_CUDA(cudaMemcpyAsync(h->rays.ptr, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (iptTraceRaysDevice(scene, (const float*)h->rays.ptr, n, (int*)h->hits_tri.ptr, (float*)h->hits_t.ptr, h->stream) != 0) return -1;
+    IPT_CUDA(cudaMemcpyAsync(tri, h->hits_tri.ptr, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    IPT_CUDA(cudaMemcpyAsync(t, h->hits_t.ptr, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    IPT_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+  });
 }
 
 int iptRenderDevice(void* scene, const IptRenderParams* p, float* img_dev, unsigned char* img8_dev, unsigned long long* counters_dev,
@@ -873,45 +915,52 @@ int iptRenderDevice(void* scene, const IptRenderParams* p, float* img_dev, unsig
 }
 
 int iptRender(void* scene, const IptRenderParams* p, float* img, unsigned char* img8, unsigned long long* counters) {
-  SceneHandle* h = checked_device(scene);
-  if (!h) return -1;
-  Plan plan;
-  if (make_plan(h, p, &plan) != 0) return -1;
-  std::lock_guard<std::recursive_mutex> lk(h->mutex);
-  IPT_CUDA(cudaSetDevice(h->device));
-  const size_t n3 = (size_t)plan.rp.n_pix * 3;
-  IPT_CUDA(h->img.reserve(n3 * sizeof(float)));
-  IPT_CUDA(h->img8.reserve(n3));
-  IPT_CUDA(h->cnt_out.reserve(4 * sizeof(unsigned long long)));
-  unsigned long long* cdev = (unsigned long long*)h->cnt_out.ptr;
-  if (launch_forward(h, plan, img ? (float*)h->img.ptr : nullptr, img8 ? (unsigned char*)h->img8.ptr : nullptr, cdev, h->stream) != 0) return -1;
-  if (img) IPT_CUDA(cudaMemcpyAsync(img, h->img.ptr, n3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  if (img8) IPT_CUDA(cudaMemcpyAsync(img8, h->img8.ptr, n3, cudaMemcpyDeviceToHost, h->stream));
-  if (counters) IPT_CUDA(cudaMemcpyAsync(counters, cdev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-  IPT_CUDA(cudaStreamSynchronize(h->stream));
-  return 0;
+  return guarded("iptRender", [&]() -> int {
+    SceneHandle* h = checked_device(scene);
+    if (!h) return -1;
+    Plan plan;
+    if (make_plan(h, p, &plan) != 0) return -1;
+    std::lock_guard<std::recursive_mutex> lk(h->mutex);
+    IPT_CUDA(cudaSetDevice(h->device));
+    const size_t n3 = (size_t)plan.rp.n_pix * 3;
+    IPT_CUDA(h->img.reserve(n3 * sizeof(float)));
+    IPT_CUDA(h->img8.reserve(n3));
+    IPT_CUDA(h->cnt_out.reserve(4 * sizeof(unsigned long long)));
+    unsigned long long* cdev = (unsigned long long*)h->cnt_out.ptr;
+    if (launch_forward(h, plan, img ? (float*)h->img.ptr : nullptr, img8 ? (unsigned char*)h->img8.ptr : nullptr, cdev, h->stream) != 0) return -1;
+    if (img) IPT_CUDA(cudaMemcpyAsync(img, h->img.ptr, n3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (img8) IPT_CUDA(cudaMemcpyAsync(img8, h->img8.ptr, n3, cudaMemcpyDeviceToHost, h->stream));
+    if (counters) IPT_CUDA(cudaMemcpyAsync(counters, cdev, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    IPT_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+  });
 }
 
 int iptCreateImageEx(void* scene, const IptRenderParams* p, const char* png_path) {
-  if (!p || !png_path) return fail("iptCreateImageEx: bad arguments");
-  IptRenderParams q = *p;
-  q.row_begin = 0;
-  q.row_end = 0;
-  q.row_step = 1;
-  std::vector<unsigned char> px((size_t)q.width * q.height * 3);
-  if (iptRender(scene, &q, nullptr, px.data(), nullptr) != 0) return -1;
-  std::string err;
-  if (!write_png_rgb8(png_path, px.data(), q.width, q.height, &err)) return fail(err);
-  return 0;
+  return guarded("iptCreateImageEx", [&]() -> int {
+    if (!p || !png_path) return fail("iptCreateImageEx: bad arguments");
+    IptRenderParams q = *p;
+    q.row_begin = 0;
+    q.row_end = 0;
+    q.row_step = 1;
+    std::vector<unsigned char> px((size_t)q.width * q.height * 3);
+    if (iptRender(scene, &q, nullptr, px.data(), nullptr) != 0) return -1;
+    std::string err;
+    if (!write_png_rgb8(png_path, px.data(), q.width, q.height, &err)) return fail(err);
+    return 0;
+  });
 }
 
 void createImage(void* scenePtr, char* img_file) {
-  IptRenderParams p;
-  iptDefaultParams(&p);
-  const uint64_t seed = legacy_seed();
-  p.seed_lo = (uint32_t)seed;
-  p.seed_hi = (uint32_t)(seed >> 32);
-  if (iptCreateImageEx(scenePtr, &p, img_file) != 0) fprintf(stderr, "ipt_b200: createImage failed: %s\n", g_error.c_str());
+  guarded("createImage", [&]() -> int {
+    IptRenderParams p;
+    iptDefaultParams(&p);
+    const uint64_t seed = legacy_seed();
+    p.seed_lo = (uint32_t)seed;
+    p.seed_hi = (uint32_t)(seed >> 32);
+    if (iptCreateImageEx(scenePtr, &p, img_file) != 0) fprintf(stderr, "ipt_b200: createImage failed: %s\n", g_error.c_str());
+    return 0;
+  });
 }
 
 int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsigned char* target_dev, double* raw_dev, void* stream) {
@@ -925,6 +974,10 @@ int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsign
   cudaStream_t st = (cudaStream_t)stream;
   const DevScene sc = h->dev();
   const int nT = sc.nT;
+  // the edge matrix is dense, (nT + 1) x nT (inv_scene.h:52-65): refuse scenes whose matrix does not fit 32-bit indexing
+  // of the accumulators (nT <= 14 000 keeps (nT + 1) nT x 10 floats below 2^31) instead of wrapping
+  if ((size_t)(nT + 1) * (size_t)nT * kGraphAccPerEdge >= ((size_t)1 << 31))
+    return fail("createGraph: the scene is too large for the dense (nT + 1) x nT edge matrix of the reference (nT must stay below 14 000)");
   const int n_edges = (nT + 1) * nT;
   const int acc_floats = n_edges * kGraphAccPerEdge;
   IPT_CUDA(cudaMemsetAsync(raw_dev, 0, (size_t)n_edges * 16 * sizeof(double), st));
@@ -1011,45 +1064,50 @@ int iptGraphCompressDevice(const double* raw_dev, int nT, float* data_dev, void*
 
 int iptCreateGraphEx(void* scene, const IptRenderParams* p, const unsigned char* target, double* raw, float* data,
                      unsigned long long* counters) {
-  SceneHandle* h = checked_device(scene);
-  if (!h) return -1;
-  if (!p || !target) return fail("iptCreateGraphEx: bad arguments");
-  std::lock_guard<std::recursive_mutex> lk(h->mutex);
-  IPT_CUDA(cudaSetDevice(h->device));
-  const int nT = (int)h->host.tris.size();
-  const size_t n_edges = (size_t)(nT + 1) * nT;
-  const size_t tbytes = (size_t)p->width * p->height * 3;
-  IPT_CUDA(h->target.reserve(tbytes));
-  IPT_CUDA(h->raw.reserve(std::max<size_t>(n_edges, 1) * 16 * sizeof(double)));
-  IPT_CUDA(cudaMemcpyAsync(h->target.ptr, target, tbytes, cudaMemcpyHostToDevice, h->stream));
-  if (iptGraphAccumulateDevice(scene, p, (const unsigned char*)h->target.ptr, (double*)h->raw.ptr, h->stream) != 0) return -1;
-  std::vector<double> host_raw(n_edges * 16);
-  if (n_edges) IPT_CUDA(cudaMemcpyAsync(host_raw.data(), h->raw.ptr, n_edges * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (counters) IPT_CUDA(cudaMemcpyAsync(counters, h->counters.ptr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-  IPT_CUDA(cudaStreamSynchronize(h->stream));
-  if (raw && n_edges) memcpy(raw, host_raw.data(), n_edges * 16 * sizeof(double));
-  if (data) return iptGraphCompress(host_raw.data(), nT, data);
-  return 0;
+  return guarded("iptCreateGraphEx", [&]() -> int {
+    SceneHandle* h = checked_device(scene);
+    if (!h) return -1;
+    if (!p || !target) return fail("iptCreateGraphEx: bad arguments");
+    std::lock_guard<std::recursive_mutex> lk(h->mutex);
+    IPT_CUDA(cudaSetDevice(h->device));
+    const int nT = (int)h->host.tris.size();
+    const size_t n_edges = (size_t)(nT + 1) * nT;
+    const size_t tbytes = (size_t)p->width * p->height * 3;
+    IPT_CUDA(h->target.reserve(tbytes));
+    IPT_CUDA(h->raw.reserve(std::max<size_t>(n_edges, 1) * 16 * sizeof(double)));
+    IPT_CUDA(cudaMemcpyAsync(h->target.ptr, target, tbytes, cudaMemcpyHostToDevice, h->stream));
+    if (iptGraphAccumulateDevice(scene, p, (const unsigned char*)h->target.ptr, (double*)h->raw.ptr, h->stream) != 0) return -1;
+    std::vector<double> host_raw(n_edges * 16);
+    if (n_edges) IPT_CUDA(cudaMemcpyAsync(host_raw.data(), h->raw.ptr, n_edges * 16 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (counters) IPT_CUDA(cudaMemcpyAsync(counters, h->counters.ptr, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    IPT_CUDA(cudaStreamSynchronize(h->stream));
+    if (raw && n_edges) memcpy(raw, host_raw.data(), n_edges * 16 * sizeof(double));
+    if (data) return iptGraphCompress(host_raw.data(), nT, data);
+    return 0;
+  });
 }
 
 void createGraph(void* scenePtr, char* imgFile, float* data) {
-  SceneHandle* h = checked_device(scenePtr);
-  if (!h || !imgFile || !data) { fprintf(stderr, "ipt_b200: createGraph: bad arguments\n"); return; }
-  IptRenderParams p;
-  iptDefaultParams(&p);
-  const uint64_t seed = legacy_seed();
-  p.seed_lo = (uint32_t)seed;
-  p.seed_hi = (uint32_t)(seed >> 32);
-  std::vector<unsigned char> target;
-  int w = 0, hgt = 0;
-  std::string err;
-  if (!read_png_rgb8(imgFile, &target, &w, &hgt, &err)) { fail(err); fprintf(stderr, "ipt_b200: createGraph: %s\n", err.c_str()); return; }
-  if (w != p.width || hgt != p.height) {   // the reference silently assumes 500x500 (inv_scene.h:57)
-    fail("createGraph: target image must be 500x500");
-    fprintf(stderr, "ipt_b200: %s (got %dx%d)\n", g_error.c_str(), w, hgt);
-    return;
-  }
-  if (iptCreateGraphEx(scenePtr, &p, target.data(), nullptr, data, nullptr) != 0) fprintf(stderr, "ipt_b200: createGraph failed: %s\n", g_error.c_str());
+  guarded("createGraph", [&]() -> int {
+    SceneHandle* h = checked_device(scenePtr);
+    if (!h || !imgFile || !data) { fprintf(stderr, "ipt_b200: createGraph: bad arguments\n"); return 0; }
+    IptRenderParams p;
+    iptDefaultParams(&p);
+    const uint64_t seed = legacy_seed();
+    p.seed_lo = (uint32_t)seed;
+    p.seed_hi = (uint32_t)(seed >> 32);
+    std::vector<unsigned char> target;
+    int w = 0, hgt = 0;
+    std::string err;
+    if (!read_png_rgb8(imgFile, &target, &w, &hgt, &err)) { fail(err); fprintf(stderr, "ipt_b200: createGraph: %s\n", err.c_str()); return 0; }
+    if (w != p.width || hgt != p.height) {   // the reference silently assumes 500x500 (inv_scene.h:57)
+      fail("createGraph: target image must be 500x500");
+      fprintf(stderr, "ipt_b200: %s (got %dx%d)\n", g_error.c_str(), w, hgt);
+      return 0;
+    }
+    if (iptCreateGraphEx(scenePtr, &p, target.data(), nullptr, data, nullptr) != 0) fprintf(stderr, "ipt_b200: createGraph failed: %s\n", g_error.c_str());
+    return 0;
+  });
 }
 
 int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned char* target_dev, double* lossgrad_dev, float* img_dev,
@@ -1083,28 +1141,30 @@ int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned ch
 }
 
 int iptRenderGrad(void* scene, const IptRenderParams* p, const unsigned char* target, double* loss, double* grad, float* img) {
-  SceneHandle* h = checked_device(scene);
-  if (!h) return -1;
-  if (!p || !target || !loss || !grad) return fail("iptRenderGrad: bad arguments");
-  std::lock_guard<std::recursive_mutex> lk(h->mutex);
-  IPT_CUDA(cudaSetDevice(h->device));
-  const int nT = (int)h->host.tris.size();
-  Plan plan;
-  if (make_plan(h, p, &plan) != 0) return -1;
-  const size_t tbytes = (size_t)p->width * p->height * 3;
-  const size_t n3 = (size_t)plan.rp.n_pix * 3;
-  IPT_CUDA(h->target.reserve(tbytes));
-  IPT_CUDA(h->lossgrad.reserve((size_t)(1 + 3 * nT) * sizeof(double)));
-  IPT_CUDA(h->img.reserve(n3 * sizeof(float)));
-  IPT_CUDA(cudaMemcpyAsync(h->target.ptr, target, tbytes, cudaMemcpyHostToDevice, h->stream));
-  if (iptRenderGradDevice(scene, p, (const unsigned char*)h->target.ptr, (double*)h->lossgrad.ptr, (float*)h->img.ptr, h->stream) != 0) return -1;
-  std::vector<double> lg(1 + 3 * (size_t)nT);
-  IPT_CUDA(cudaMemcpyAsync(lg.data(), h->lossgrad.ptr, lg.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (img) IPT_CUDA(cudaMemcpyAsync(img, h->img.ptr, n3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  IPT_CUDA(cudaStreamSynchronize(h->stream));
-  *loss = lg[0];
-  memcpy(grad, lg.data() + 1, 3 * (size_t)nT * sizeof(double));
-  return 0;
+  return guarded("iptRenderGrad", [&]() -> int {
+    SceneHandle* h = checked_device(scene);
+    if (!h) return -1;
+    if (!p || !target || !loss || !grad) return fail("iptRenderGrad: bad arguments");
+    std::lock_guard<std::recursive_mutex> lk(h->mutex);
+    IPT_CUDA(cudaSetDevice(h->device));
+    const int nT = (int)h->host.tris.size();
+    Plan plan;
+    if (make_plan(h, p, &plan) != 0) return -1;
+    const size_t tbytes = (size_t)p->width * p->height * 3;
+    const size_t n3 = (size_t)plan.rp.n_pix * 3;
+    IPT_CUDA(h->target.reserve(tbytes));
+    IPT_CUDA(h->lossgrad.reserve((size_t)(1 + 3 * nT) * sizeof(double)));
+    IPT_CUDA(h->img.reserve(n3 * sizeof(float)));
+    IPT_CUDA(cudaMemcpyAsync(h->target.ptr, target, tbytes, cudaMemcpyHostToDevice, h->stream));
+    if (iptRenderGradDevice(scene, p, (const unsigned char*)h->target.ptr, (double*)h->lossgrad.ptr, (float*)h->img.ptr, h->stream) != 0) return -1;
+    std::vector<double> lg(1 + 3 * (size_t)nT);
+    IPT_CUDA(cudaMemcpyAsync(lg.data(), h->lossgrad.ptr, lg.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (img) IPT_CUDA(cudaMemcpyAsync(img, h->img.ptr, n3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    IPT_CUDA(cudaStreamSynchronize(h->stream));
+    *loss = lg[0];
+    memcpy(grad, lg.data() + 1, 3 * (size_t)nT * sizeof(double));
+    return 0;
+  });
 }
 
 int iptPathKernelTimes(void* scene, float* ms, int max_count) {
@@ -1131,42 +1191,48 @@ int iptLastCounters(void* scene, unsigned long long* counters) {
 }
 
 int iptBuildBVH(const float* boxes, const float* pos, int n, int leaf_size, float* node_boxes, int* node_ints, int max_nodes, int* perm) {
-  if (n < 0 || (n > 0 && (!boxes || !pos || !perm)) || !node_boxes || !node_ints) return fail("iptBuildBVH: bad arguments");
-  std::vector<BvhNodeHost> nodes;
-  std::vector<int> pm;
-  std::string err;
-  int dev = g_device;
-  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) dev = -1;
-  if (!build_bvh(boxes, pos, n, leaf_size, &nodes, &pm, dev, &err)) return fail(err);
-  if ((int)nodes.size() > max_nodes) return fail("iptBuildBVH: max_nodes too small");
-  for (size_t i = 0; i < nodes.size(); i++) {
-    for (int k = 0; k < 3; k++) { node_boxes[6 * i + k] = nodes[i].lo[k]; node_boxes[6 * i + 3 + k] = nodes[i].hi[k]; }
-    node_ints[3 * i] = nodes[i].start; node_ints[3 * i + 1] = nodes[i].nPrims; node_ints[3 * i + 2] = nodes[i].rightOffset;
-  }
-  for (int i = 0; i < n; i++) perm[i] = pm[i];
-  return (int)nodes.size();
+  return guarded("iptBuildBVH", [&]() -> int {
+    if (n < 0 || (n > 0 && (!boxes || !pos || !perm)) || !node_boxes || !node_ints) return fail("iptBuildBVH: bad arguments");
+    std::vector<BvhNodeHost> nodes;
+    std::vector<int> pm;
+    std::string err;
+    int dev = g_device;
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+    if (!build_bvh(boxes, pos, n, leaf_size, &nodes, &pm, dev, &err)) return fail(err);
+    if ((int)nodes.size() > max_nodes) return fail("iptBuildBVH: max_nodes too small");
+    for (size_t i = 0; i < nodes.size(); i++) {
+      for (int k = 0; k < 3; k++) { node_boxes[6 * i + k] = nodes[i].lo[k]; node_boxes[6 * i + 3 + k] = nodes[i].hi[k]; }
+      node_ints[3 * i] = nodes[i].start; node_ints[3 * i + 1] = nodes[i].nPrims; node_ints[3 * i + 2] = nodes[i].rightOffset;
+    }
+    for (int i = 0; i < n; i++) perm[i] = pm[i];
+    return (int)nodes.size();
+  });
 }
 
 int iptWritePNG(const char* path, const unsigned char* rgb, int width, int height) {
-  std::string err;
-  if (!path || !rgb || width <= 0 || height <= 0) return fail("iptWritePNG: bad arguments");
-  if (!write_png_rgb8(path, rgb, width, height, &err)) return fail(err);
-  return 0;
+  return guarded("iptWritePNG", [&]() -> int {
+    std::string err;
+    if (!path || !rgb || width <= 0 || height <= 0) return fail("iptWritePNG: bad arguments");
+    if (!write_png_rgb8(path, rgb, width, height, &err)) return fail(err);
+    return 0;
+  });
 }
 
 int iptReadPNG(const char* path, unsigned char* rgb, int capacity_bytes, int* width, int* height) {
-  std::string err;
-  std::vector<unsigned char> px;
-  int w = 0, h = 0;
-  if (!path) return fail("iptReadPNG: bad arguments");
-  if (!read_png_rgb8(path, &px, &w, &h, &err)) return fail(err);
-  if (width) *width = w;
-  if (height) *height = h;
-  if (rgb) {
-    if ((size_t)capacity_bytes < px.size()) return fail("iptReadPNG: buffer too small");
-    memcpy(rgb, px.data(), px.size());
-  }
-  return 0;
+  return guarded("iptReadPNG", [&]() -> int {
+    std::string err;
+    std::vector<unsigned char> px;
+    int w = 0, h = 0;
+    if (!path) return fail("iptReadPNG: bad arguments");
+    if (!read_png_rgb8(path, &px, &w, &h, &err)) return fail(err);
+    if (width) *width = w;
+    if (height) *height = h;
+    if (rgb) {
+      if ((size_t)capacity_bytes < px.size()) return fail("iptReadPNG: buffer too small");
+      memcpy(rgb, px.data(), px.size());
+    }
+    return 0;
+  });
 }
 
 }  // extern "C"

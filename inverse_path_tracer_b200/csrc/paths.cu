@@ -353,7 +353,9 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
           const float u_pick = u16(rn.x >> 16), r1 = u16(rn.y >> 16), r2 = u16(rn.y & 0xffffu);
           int li = 0;
           if (BVH) {
-            li = pick_light(slight, nE, u_pick);
+            float up = u_pick;
+            if (nE > IPT_LIGHT_PICK16_MAX) up = u01(philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_PICK, rp.keys).x);
+            li = pick_light(slight, nE, up);
           } else {
             // pick_light's linear scan (path_trace.cu:39-51) over the shared-memory table (brute-force scenes have <= 128 lights)
             while (li < nE - 1 && !(lds1f(slight_a + (uint32_t)(3 * li) * 16u + 12u) >= u_pick)) li++;

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -58,7 +59,16 @@ bool write_png_rgb8(const char* path, const unsigned char* rgb, int w, int h, st
   return true;
 }
 
+static bool read_png_rgb8_impl(const char* path, std::vector<unsigned char>* rgb, int* w, int* h, std::string* err);
 bool read_png_rgb8(const char* path, std::vector<unsigned char>* rgb, int* w, int* h, std::string* err) {
+  try {
+    return read_png_rgb8_impl(path, rgb, w, h, err);
+  } catch (const std::exception& e) {   // bad_alloc and friends must not cross the C ABI
+    *err = std::string("png: ") + e.what();
+    return false;
+  }
+}
+static bool read_png_rgb8_impl(const char* path, std::vector<unsigned char>* rgb, int* w, int* h, std::string* err) {
   FILE* f = fopen(path, "rb");
   if (!f) { *err = std::string("png: cannot open: ") + path; return false; }
   std::vector<unsigned char> buf;
@@ -77,6 +87,7 @@ bool read_png_rgb8(const char* path, std::vector<unsigned char>* rgb, int* w, in
     const unsigned char* data = &buf[pos + 8];
     if (pos + 12 + (size_t)len > buf.size()) { *err = "png: truncated chunk"; return false; }
     if (!memcmp(type, "IHDR", 4)) {
+      if (len < 13) { *err = "png: short IHDR chunk"; return false; }
       W = (int)get32(data); H = (int)get32(data + 4); depth = data[8]; ctype = data[9]; interlace = data[12];
     } else if (!memcmp(type, "PLTE", 4)) {
       palette.assign(data, data + len);
@@ -88,6 +99,8 @@ bool read_png_rgb8(const char* path, std::vector<unsigned char>* rgb, int* w, in
     pos += 12 + (size_t)len;
   }
   if (W <= 0 || H <= 0) { *err = "png: missing IHDR"; return false; }
+  // files come from callers (createGraph takes a path): a corrupt header must not turn into a multi-gigabyte allocation
+  if (W > 32768 || H > 32768 || (long long)W * H > (1ll << 28)) { *err = "png: image larger than 32768 x 32768 / 2^28 pixels"; return false; }
   if (interlace != 0) { *err = "png: interlaced images are not supported"; return false; }
   if (depth != 8 && depth != 16) { *err = "png: only 8/16-bit samples are supported"; return false; }
   int ch = (ctype == 0) ? 1 : (ctype == 2) ? 3 : (ctype == 3) ? 1 : (ctype == 4) ? 2 : (ctype == 6) ? 4 : 0;

@@ -74,11 +74,11 @@ struct SceneHandle {
   // counter and the event ring are per handle), and calls enqueued on DIFFERENT streams are chained through `busy`
   // (recorded after each call, waited on by the next), so two calls in flight on one scene cannot share scratch.
   std::recursive_mutex mutex;
-  // chunked launches (api.cu): internal streams and fork / join events; `chunks` = 0 picks the count from the launch size
+  // chunked launches (api.cu; measured slower, off unless IPT_CHUNKS asks): internal streams and fork / join events
   static constexpr int kMaxChunks = 4;
   cudaStream_t cstream[kMaxChunks] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxChunks] = {};
-  int chunks = 0;
+  int chunks = 1;
   cudaEvent_t busy = nullptr;
   bool busy_recorded = false;
   cudaStream_t busy_stream = nullptr;

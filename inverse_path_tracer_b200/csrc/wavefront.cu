@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(kWfBlock, IPT_WF_MINB) k_wf_shade(DevScene sc,
           const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.keys);
           if (nE > 0) {
             const float u_pick = u16(rn.x >> 16), r1 = u16(rn.y >> 16), r2 = u16(rn.y & 0xffffu);
-            const int li = pick_light(slight, nE, u_pick);
+            float up = u_pick;
+            if (nE > IPT_LIGHT_PICK16_MAX) up = u01(philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_PICK, rp.keys).x);
+            const int li = pick_light(slight, nE, up);
             const float4 la = __ldg(&slight[3 * li]), lb = __ldg(&slight[3 * li + 1]), lc = __ldg(&slight[3 * li + 2]);
             const float sq = sqrtf(r1);
             const float c1 = 1.0f - sq, c2 = sq * (1.0f - r2), c3 = r2 * sq;

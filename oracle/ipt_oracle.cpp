@@ -104,6 +104,7 @@ static inline float u01(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-
 static inline float u16(uint32_t x) { return fmaf((float)x, 1.52587890625e-05f, 7.62939453125e-06f); }
 
 enum { STREAM_CAMERA = 0, STREAM_BOUNCE = 1 };
+static bool g_canon_v1_draws = false;   // test switch, see Rng::draw_bounce
 struct Rng {
   uint32_t key[2];
   uint32_t pixel, sample;
@@ -116,9 +117,25 @@ struct Rng {
   // one Philox call per bounce (canon v3), in the reference's draw order (path_trace.cu:43,55-56,130,93-94):
   //   word0 = [light pick : 16 | Russian roulette : 16], word1 = [r1 : 16 | r2 : 16], word2 = phi, word3 = theta
   // un = {pick, r1, r2, rr}, ud = {phi, theta}
+  // scenes with more than 4096 emissive triangles (an emissive mesh) pick the light with a full 32-bit uniform from its
+  // own call (stream 2): 16 bits could never select most of 10^5 lights (ipt_math.cuh, IPT_STREAM_PICK)
+  float draw_pick32(uint32_t bounce) const {
+    uint32_t ctr[4] = {pixel, sample, bounce, 2u}, o[4];
+    philox4x32_10(ctr, key, o);
+    return u01(o[0]);
+  }
   void draw_bounce(uint32_t bounce, float un[4], float ud[2]) const {
     uint32_t ctr[4] = {pixel, sample, bounce, STREAM_BOUNCE}, o[4];
     philox4x32_10(ctr, key, o);
+    if (g_canon_v1_draws) {
+      // canon v1 (kept for one test, orc_set_canon_v1_draws): six full 32-bit uniforms per bounce like the reference's six
+      // curand_uniform calls, from two Philox calls.  tests/test_oracle.py bounds the difference to canon v3 below.
+      uint32_t ctr2[4] = {pixel, sample, bounce, 2u}, o2[4];
+      philox4x32_10(ctr2, key, o2);
+      un[0] = u01(o[0]); un[1] = u01(o[1]); un[2] = u01(o[2]); un[3] = u01(o[3]);
+      ud[0] = u01(o2[0]); ud[1] = u01(o2[1]);
+      return;
+    }
     un[0] = u16(o[0] >> 16); un[3] = u16(o[0] & 0xffffu);
     un[1] = u16(o[1] >> 16); un[2] = u16(o[1] & 0xffffu);
     ud[0] = u01(o[2]); ud[1] = u01(o[3]);
@@ -1083,6 +1100,7 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
       // directLighting, path_trace.cu:30-89
       float un[4], ud[2];
       rng.draw_bounce((uint32_t)recursion, un, ud);
+      if (nE > 4096 && !g_canon_v1_draws) un[0] = rng.draw_pick32((uint32_t)recursion);
       L_d[0] = L_d[1] = L_d[2] = 0.0f;
       if (nE > 0) {
         LightSample ls;
@@ -1215,6 +1233,7 @@ static void graph_sample(const Scene& sc, const Params& P, int r, int c, int sam
     const Triangle& tri = sc.tri(isect.tri);
     float un[4], ud[2];
     rng.draw_bounce((uint32_t)recursion, un, ud);
+      if (nE > 4096 && !g_canon_v1_draws) un[0] = rng.draw_pick32((uint32_t)recursion);
     bool isSpecular = false;   // curand_uniform(&state) < P_SPEC with P_SPEC == 0 (inv_path_trace.cu:117): never true, not drawn
     int src = tri.idx;
     edges[(size_t)dst * nT + src].update(weight, pixel, zero, factors);
@@ -1273,6 +1292,8 @@ static void graph_compress(const std::vector<Edge>& edges, int nT, float* data) 
 using namespace orc;
 
 extern "C" {
+
+void orc_set_canon_v1_draws(int on) { g_canon_v1_draws = on != 0; }
 float orc_canon_pow(float x, float y) { return orc::canon_pow(x, y); }
 float orc_canon_logf(float x) { return orc::canon_logf(x); }
 
