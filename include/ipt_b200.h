@@ -125,9 +125,9 @@ int iptGraphCompress(const double* raw, int n_triangles, float* data);
 int iptGraphCompressDevice(const double* raw_dev, int n_triangles, float* data_dev, void* stream);
 
 /* NEW (no reference counterpart): loss = sum over the shard of (L/(1+L) - target/255)^2 / (3*W*H) and
- * its gradient with respect to every diffuse albedo, nT*3 doubles.  max_depth is clamped to 64.  Exact for the
- * materials the reference ships (Ks == 0): the estimator is then a polynomial in the albedos.  With a Phong lobe
- * (Ks != 0) the loss is still exact, the gradient keeps only the diffuse factor of each bounce's throughput. */
+ * its gradient with respect to every diffuse albedo, nT*3 doubles.  max_depth is clamped to 64.  The sampler does
+ * not depend on Kd, so the estimator is a polynomial in the albedos and its gradient is exact -- with a Phong lobe
+ * (Ks != 0) too: the adjoint then records the per-channel throughput factor and direct BSDF of every bounce. */
 int iptRenderGrad(void* scene, const IptRenderParams* p, const unsigned char* target, double* loss, double* grad, float* img);
 /* device buffers: lossgrad_dev[1 + nT*3] doubles (loss first), img_dev optional; asynchronous */
 int iptRenderGradDevice(void* scene, const IptRenderParams* p, const unsigned char* target_dev, double* lossgrad_dev,

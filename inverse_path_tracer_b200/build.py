@@ -21,7 +21,7 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libipt_b200.so")
 
 SOURCES = ["api.cu", "inverse.cu", "paths.cu", "trace.cu", "wavefront.cu", "bvh_build.cu", "scene_host.cu", "png_io.cpp"]
-HEADERS = ["ipt_math.cuh", "intersect.cuh", "shading.cuh", "device_scene.h", "kernels.h", "scene_host.h", "scene_handle.h", os.path.join(ROOT, "include", "ipt_b200.h")]
+HEADERS = ["ipt_math.cuh", "intersect.cuh", "shading.cuh", "device_scene.h", "kernels.h", "scene_host.h", "scene_handle.h", "nvtx_ranges.h", os.path.join(ROOT, "include", "ipt_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]

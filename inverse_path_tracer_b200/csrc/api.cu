@@ -23,6 +23,7 @@
 #include "device_scene.h"
 #include "kernels.h"
 #include "scene_handle.h"
+#include "nvtx_ranges.h"
 #include "ipt_math.cuh"
 
 namespace ipt {
@@ -433,7 +434,10 @@ int forward_chunk(SceneHandle* h, const Plan& plan, const DevScene& sc, int c, i
   out.partial = (float*)h->partial.ptr + (size_t)lr0 * rp.width * rp.groups * 3;
   const size_t smem = paths_smem_bytes(sc, 0);
   const int grid = h->sm_count * paths_blocks_per_sm(MODE_RENDER_ID, sc, smem);
-  IPT_CUDA(launch_paths(MODE_RENDER_ID, sc, rp, out, grid, smem, st_c));
+  {
+    NvtxRange r("ipt.paths.render");
+    IPT_CUDA(launch_paths(MODE_RENDER_ID, sc, rp, out, grid, smem, st_c));
+  }
   g_launches += 1;
   return 0;
 }
@@ -496,7 +500,7 @@ int prepare_grad(SceneHandle* h, const Plan& plan, int k, GradLaunch* g) {
   if (g->acc_mode) IPT_CUDA(h->block_acc.reserve((size_t)k * g->grid * 3 * nT * sizeof(float)));
   // adjoint vertex stacks: two halves of max_depth 32-byte vertices per resident thread (no initialisation needed:
   // a sweep only reads what its own path wrote)
-  g->vstack_bytes = (size_t)g->grid * paths_block_threads() * 2 * (size_t)g->vdepth * 32;
+  g->vstack_bytes = (size_t)g->grid * paths_block_threads() * 2 * (size_t)g->vdepth * (sc.plain ? 32 : 64);   // 64-byte vertices carry the Phong factors
   IPT_CUDA(h->vstacks.reserve((size_t)k * g->vstack_bytes));
   return 0;
 }
@@ -526,7 +530,10 @@ int grad_chunk(SceneHandle* h, const Plan& plan, const DevScene& sc, const GradL
   }
   out.vdepth = g.vdepth;
   out.vstacks = (float4*)((char*)h->vstacks.ptr + (size_t)c * g.vstack_bytes);
-  IPT_CUDA(launch_paths(MODE_GRAD_ID, sc, rp, out, g.grid, g.smem, st_c));
+  {
+    NvtxRange r("ipt.paths.adjoint");
+    IPT_CUDA(launch_paths(MODE_GRAD_ID, sc, rp, out, g.grid, g.smem, st_c));
+  }
   g_launches += 1;
   return 0;
 }
@@ -1013,6 +1020,7 @@ int iptGraphAccumulateDevice(void* scene, const IptRenderParams* p, const unsign
   {
     const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
     IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
+    NvtxRange r("ipt.paths.graph");
     IPT_CUDA(launch_paths(MODE_GRAPH_ID, sc, plan.rp, out, grid, smem, st));
     IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
     h->ev_count++;

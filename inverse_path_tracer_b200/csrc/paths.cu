@@ -26,8 +26,12 @@ namespace ipt {
 //   a = {tri (int bits), b, light (int bits), g}     b_ = {P0, P1, P2, unused}
 // The stacks live in global memory laid out by the kernel (k_paths, MODE_GRAD) so that one vertex is one
 // sector; as a thread-local array every 4-byte field of a vertex lands in a different 128-byte line.
+// Scenes with a Phong lobe or per-vertex normals (template PLAIN == false) record two more words, 64 bytes in all:
+//   t = {T0, T1, T2, -}  per-channel throughput factor of the bounce, (Kd/pi + Ks phong) * coeff  (0 when the path ended)
+//   d = {f0, f1, f2, -}  BSDF(isDirect = true) of the bounce, Kd + Ks phong
+// so that the backward sweep Pbar_k = C_k + T_k Pbar_{k+1} is exact for them too (plain scenes rebuild both from Kd).
 struct AdjVertex {
-  float4 a, p;
+  float4 a, p, t, d;
 };
 __device__ __forceinline__ int adj_tri(const AdjVertex& v) { return __float_as_int(v.a.x); }
 __device__ __forceinline__ int adj_light(const AdjVertex& v) { return __float_as_int(v.a.z); }
@@ -64,6 +68,9 @@ constexpr uint32_t kRingStride = kBlock * 16u;   // bytes between two slots of o
 #define IPT_NORMALIZE(v) normalize3(v)
 #define IPT_SQRT_UNIT(x) sqrtf(x)
 #define IPT_SQRT(x) sqrtf(x)
+#endif
+#ifndef IPT_SWEEP_MATCH
+#define IPT_SWEEP_MATCH 0     // __match_any_sync pre-reduction of the adjoint's gradient atomics: measured, not faster (profiles/r02_adjoint_ab.txt)
 #endif
 #ifndef IPT_SWEEP_PER_TRIP
 #define IPT_SWEEP_PER_TRIP 3
@@ -149,10 +156,12 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   int gdst = 0;
   float pix0 = 0.0f, pix1 = 0.0f, pix2 = 0.0f;
   // grad mode
-  // vertex stacks: slot s of this lane is the 32 bytes at vw + s * 64 (float4 units); two halves of vdepth slots:
+  // vertex stacks: slot s of this lane is the 32 (plain scenes) / 64 bytes at vw + s * kVS (float4 units); two halves of vdepth slots:
   // path being recorded / path being swept
   float4* vw = nullptr;
-  if (MODE == MODE_GRAD) vw = out.vstacks + ((size_t)(blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * (2 * out.vdepth) * 32 + lane) * 2;
+  constexpr int kVF4 = PLAIN ? 2 : 4;       // float4 words per recorded vertex
+  constexpr int kVS = 32 * kVF4;            // float4 distance between two slots of one lane
+  if (MODE == MODE_GRAD) vw = out.vstacks + ((size_t)(blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5)) * (2 * out.vdepth) * 32 + lane) * kVF4;
   int vbuf = 0;                              // first slot of the half the path in flight records into
   int sw_buf = 0, sw_k = -1;                 // pending sweep: its half, next vertex to process (-1: none)
   bool fin_wait = false;                     // a finished path waits for the pending sweep before it can be parked
@@ -183,10 +192,11 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   // stacks while 30 wait): it is parked in the lane's other stack half and advanced kSweepPerTrip vertices per
   // trip of the main loop, where most lanes of the warp have one pending.
   auto sweep_step = [&]() {
-    const float4* vs = vw + (size_t)sw_buf * 64;
+    const float4* vs = vw + (size_t)sw_buf * kVS;
     const int k = sw_k--;
     AdjVertex v;
-    v.a = vs[k * 64]; v.p = vs[k * 64 + 1];
+    v.a = vs[k * kVS]; v.p = vs[k * kVS + 1];
+    if (!PLAIN) { v.t = vs[k * kVS + 2]; v.d = vs[k * kVS + 3]; }
     const int vtri = adj_tri(v);
     if (vtri >= 0) {
       const float4 kd = M(0, vtri);
@@ -194,17 +204,40 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       const float vb = v.a.y, vg = v.a.w;
       float k0 = 0.0f, k1 = 0.0f, k2 = 0.0f;   // Ke_light * g
       if (vlight >= 0) { const float4 lke = M(1, vlight); k0 = lke.x * vg; k1 = lke.y * vg; k2 = lke.z * vg; }
-      const float g0 = v.p.x * fmaf(vb, pb0, k0), g1 = v.p.y * fmaf(vb, pb1, k1), g2 = v.p.z * fmaf(vb, pb2, k2);
+      float g0 = v.p.x * fmaf(vb, pb0, k0), g1 = v.p.y * fmaf(vb, pb1, k1), g2 = v.p.z * fmaf(vb, pb2, k2);
+#if IPT_SWEEP_MATCH
+      // warp pre-reduction before the atomics (A/B, profiles/r02_adjoint_ab.txt): lanes of this sweep step that update the
+      // same triangle sum their contributions by shuffles and the lowest of them issues the three reductions
+      g0 *= sw0; g1 *= sw1; g2 *= sw2;
+      const unsigned peers = __match_any_sync(__activemask(), vtri);
+      const int leader = __ffs(peers) - 1;
+      for (unsigned rest = peers & (peers - 1u); rest; rest &= rest - 1u) {
+        const int src = __ffs(rest) - 1;
+        const float b0 = __shfl_sync(peers, g0, src), b1 = __shfl_sync(peers, g1, src), b2 = __shfl_sync(peers, g2, src);
+        if ((int)lane == leader) { g0 += b0; g1 += b1; g2 += b2; }
+      }
+      if ((int)lane == leader) {
+        if (out.acc_in_smem == 2) { float* ga = out.block_acc + (size_t)blockIdx.x * out.acc_stride + 3 * vtri; atomicAdd(ga + 0, g0); atomicAdd(ga + 1, g1); atomicAdd(ga + 2, g2); }
+        else if (out.acc_in_smem) { float* ga = sacc + 3 * vtri; atomicAdd(ga + 0, g0); atomicAdd(ga + 1, g1); atomicAdd(ga + 2, g2); }
+        else { double* gg = out.global_acc + 3 * (size_t)vtri; atomicAdd(gg + 0, (double)g0); atomicAdd(gg + 1, (double)g1); atomicAdd(gg + 2, (double)g2); }
+      }
+#else
       if (out.acc_in_smem == 2) { float* ga = out.block_acc + (size_t)blockIdx.x * out.acc_stride + 3 * vtri; atomicAdd(ga + 0, sw0 * g0); atomicAdd(ga + 1, sw1 * g1); atomicAdd(ga + 2, sw2 * g2); }
       else if (out.acc_in_smem) { float* ga = sacc + 3 * vtri; atomicAdd(ga + 0, sw0 * g0); atomicAdd(ga + 1, sw1 * g1); atomicAdd(ga + 2, sw2 * g2); }
       else { double* gg = out.global_acc + 3 * (size_t)vtri; atomicAdd(gg + 0, (double)(sw0 * g0)); atomicAdd(gg + 1, (double)(sw1 * g1)); atomicAdd(gg + 2, (double)(sw2 * g2)); }
-      pb0 = fmaf(kd.x * vb, pb0, se0 + kd.x * k0); pb1 = fmaf(kd.y * vb, pb1, se1 + kd.y * k1); pb2 = fmaf(kd.z * vb, pb2, se2 + kd.z * k2);
+#endif
+      if (PLAIN) {
+        pb0 = fmaf(kd.x * vb, pb0, se0 + kd.x * k0); pb1 = fmaf(kd.y * vb, pb1, se1 + kd.y * k1); pb2 = fmaf(kd.z * vb, pb2, se2 + kd.z * k2);
+      } else {   // recorded factors: exact with a Phong lobe as well
+        pb0 = fmaf(v.t.x, pb0, se0 + v.d.x * k0); pb1 = fmaf(v.t.y, pb1, se1 + v.d.y * k1); pb2 = fmaf(v.t.z, pb2, se2 + v.d.z * k2);
+      }
     } else {
       // miss: the stale L_d of vertex k-1 was re-added with P_k
       float c0 = se0, c1 = se1, c2 = se2;
       if (k > 0) {
         AdjVertex u;
-        u.a = vs[(k - 1) * 64];
+        u.a = vs[(k - 1) * kVS];
+        if (!PLAIN) u.d = vs[(k - 1) * kVS + 3];
         const int utri = adj_tri(u), ulight = adj_light(u);
         if (utri >= 0 && ulight >= 0) {
           const float4 lke = M(1, ulight);
@@ -214,7 +247,8 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
           if (out.acc_in_smem == 2) { float* ga = out.block_acc + (size_t)blockIdx.x * out.acc_stride + 3 * utri; atomicAdd(ga + 0, sw0 * (v.p.x * k0)); atomicAdd(ga + 1, sw1 * (v.p.y * k1)); atomicAdd(ga + 2, sw2 * (v.p.z * k2)); }
           else if (out.acc_in_smem) { float* ga = sacc + 3 * utri; atomicAdd(ga + 0, sw0 * (v.p.x * k0)); atomicAdd(ga + 1, sw1 * (v.p.y * k1)); atomicAdd(ga + 2, sw2 * (v.p.z * k2)); }
           else { double* gg = out.global_acc + 3 * (size_t)utri; atomicAdd(gg + 0, (double)(sw0 * (v.p.x * k0))); atomicAdd(gg + 1, (double)(sw1 * (v.p.y * k1))); atomicAdd(gg + 2, (double)(sw2 * (v.p.z * k2))); }
-          c0 += kd.x * k0; c1 += kd.y * k1; c2 += kd.z * k2;
+          if (PLAIN) { c0 += kd.x * k0; c1 += kd.y * k1; c2 += kd.z * k2; }
+          else { c0 += u.d.x * k0; c1 += u.d.y * k1; c2 += u.d.z * k2; }
         }
       }
       pb0 = c0; pb1 = c1; pb2 = c2;
@@ -310,7 +344,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         // miss (path_trace.cu:116): the stale L_e / L_d are re-added with the new multiplier
         if (MODE != MODE_GRAPH) { float e0, e1, e2; load_le(e0, e1, e2); L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2); }
         if (MODE == MODE_GRAD) {
-          if (bounce < out.vdepth) { float4* vp = vw + (size_t)(vbuf + bounce) * 64; vp[0] = make_float4(__int_as_float(-1), 0.0f, __int_as_float(-1), 0.0f); vp[1] = make_float4(q0, q1, q2, 0.0f); }
+          if (bounce < out.vdepth) { float4* vp = vw + (size_t)(vbuf + bounce) * kVS; vp[0] = make_float4(__int_as_float(-1), 0.0f, __int_as_float(-1), 0.0f); vp[1] = make_float4(q0, q1, q2, 0.0f); }
           path_len = bounce + 1;
         }
         finalize();
@@ -324,7 +358,10 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
         if (MODE != MODE_GRAPH && bounce == 0) e_tri = tri;
         const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.keys);
         AdjVertex vx;
-        if (MODE == MODE_GRAD) { vx.a = make_float4(__int_as_float(tri), 0.0f, __int_as_float(-1), 0.0f); vx.p = make_float4(q0, q1, q2, 0.0f); }
+        if (MODE == MODE_GRAD) {
+          vx.a = make_float4(__int_as_float(tri), 0.0f, __int_as_float(-1), 0.0f); vx.p = make_float4(q0, q1, q2, 0.0f);
+          vx.t = make_float4(0.0f, 0.0f, 0.0f, 0.0f); vx.d = vx.t;
+        }
 
         if (MODE == MODE_GRAPH) {
           // dw->update(dst, src, prev_weight, pixel, 0, prev_factors): prev_factors[DIFFUSE] == 1
@@ -379,6 +416,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
               const float co = phong_coeff(ns, rdir, toLight, ma.w);
               f0 = fmaf(mc.x, co, f0); f1 = fmaf(mc.y, co, f1); f2 = fmaf(mc.z, co, f2);
             }
+            if (MODE == MODE_GRAD) vx.d = make_float4(f0, f1, f2, 0.0f);
           }
         }
 
@@ -421,7 +459,10 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
               if (flags & TRI_SPECULAR) coeff = (cosn / p_sample) / rp.p_rr;
             }
             m0 = (m0 * i0) * coeff; m1 = (m1 * i1) * coeff; m2 = (m2 * i2) * coeff;
-            if (MODE == MODE_GRAD) vx.a.y = coeff / IPT_PI_F;
+            if (MODE == MODE_GRAD) {
+              vx.a.y = coeff / IPT_PI_F;   // d(throughput factor)/dKd, the same with or without a Phong lobe
+              if (!PLAIN) vx.t = make_float4(i0 * coeff, i1 * coeff, i2 * coeff, 0.0f);
+            }
           }
           rpos = hit;
           rdir = nd;
@@ -430,7 +471,11 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
           end_after = true;
         }
         if (MODE == MODE_GRAD) {
-          if (bounce < out.vdepth) { float4* vp = vw + (size_t)(vbuf + bounce) * 64; vp[0] = vx.a; vp[1] = vx.p; }
+          if (bounce < out.vdepth) {
+            float4* vp = vw + (size_t)(vbuf + bounce) * kVS;
+            vp[0] = vx.a; vp[1] = vx.p;
+            if (!PLAIN) { vp[2] = vx.t; vp[3] = vx.d; }
+          }
           path_len = bounce + 1;
         }
         bounce++;
@@ -544,7 +589,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
             d0 = f0 * (lmb.x * g); d1 = f1 * (lmb.y * g); d2 = f2 * (lmb.z * g);
             if (MODE == MODE_GRAD) {
               const int k = path_len - 1;   // the vertex recorded in [A] of this trip
-              if (k < out.vdepth) *reinterpret_cast<float2*>(reinterpret_cast<float*>(vw + (size_t)(vbuf + k) * 64) + 2) = make_float2(__int_as_float(sh_light), g);
+              if (k < out.vdepth) *reinterpret_cast<float2*>(reinterpret_cast<float*>(vw + (size_t)(vbuf + k) * kVS) + 2) = make_float2(__int_as_float(sh_light), g);
             }
           }
         }

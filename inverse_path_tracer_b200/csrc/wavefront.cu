@@ -3,6 +3,7 @@
 
 #include "intersect.cuh"
 #include "kernels.h"
+#include "nvtx_ranges.h"
 #include "shading.cuh"
 
 namespace ipt {
@@ -346,16 +347,25 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
         b.cap = cap; b.tile_p0 = p0; b.tile_n = tn; b.s0 = s0; b.ns = std::min(nsb, rp.spp - s0);
         const int n_paths = b.tile_n * b.ns;
         int cur = 0;
-        k_wf_generate<<<std::min((n_paths + kWfBlock - 1) / kWfBlock, shade_grid), kWfBlock, 0, st>>>(sc, rp, b, state[0], rays[0], n_live + 0, counters);
+        {
+          NvtxRange r("ipt.wavefront.generate");
+          k_wf_generate<<<std::min((n_paths + kWfBlock - 1) / kWfBlock, shade_grid), kWfBlock, 0, st>>>(sc, rp, b, state[0], rays[0], n_live + 0, counters);
+        }
         *n_launches += 1;
         for (int bounce = 0;; bounce++) {
           if (!unbounded && bounce > rp.max_depth) break;
           e = cudaMemsetAsync(n_live + (cur ^ 1), 0, sizeof(int), st);
           if (e != cudaSuccess) return e;
-          e = launch_trace_bounce(sc, rays[cur], n_live + cur, cap, hit_tri, hit_t, trace_counter, sm_count, n_launches, st);
+          {
+            NvtxRange r("ipt.wavefront.extend");
+            e = launch_trace_bounce(sc, rays[cur], n_live + cur, cap, hit_tri, hit_t, trace_counter, sm_count, n_launches, st);
+          }
           if (e != cudaSuccess) return e;
-          k_wf_shade<<<shade_grid, kWfBlock, 0, st>>>(sc, rp, b, bounce, state[cur], state[cur ^ 1], rays[cur], rays[cur ^ 1], hit_tri, hit_t, n_live + cur,
-                                                     n_live + (cur ^ 1), lsamp, counters);
+          {
+            NvtxRange r("ipt.wavefront.shade");
+            k_wf_shade<<<shade_grid, kWfBlock, 0, st>>>(sc, rp, b, bounce, state[cur], state[cur ^ 1], rays[cur], rays[cur ^ 1], hit_tri, hit_t, n_live + cur,
+                                                       n_live + (cur ^ 1), lsamp, counters);
+          }
           *n_launches += 1;
           cur ^= 1;
           if (unbounded) {
@@ -366,7 +376,10 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
             if (*host_live == 0) break;
           }
         }
-        k_wf_accumulate<<<(b.tile_n + kWfBlock - 1) / kWfBlock, kWfBlock, 0, st>>>(lsamp, b, rp.group_samples, rp.groups, rp.spp, rp.inv_spp, partial);
+        {
+          NvtxRange r("ipt.wavefront.accumulate");
+          k_wf_accumulate<<<(b.tile_n + kWfBlock - 1) / kWfBlock, kWfBlock, 0, st>>>(lsamp, b, rp.group_samples, rp.groups, rp.spp, rp.inv_spp, partial);
+        }
         *n_launches += 1;
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -1067,6 +1067,8 @@ struct Vertex {
   float g;          // cos*cos'/t^2/p_t of the visible connection (0 otherwise)
   float b;          // throughput factor excluding Kd: (1/pi) * coeff (0 when the path stopped here)
   bool cont;        // path continued past this vertex
+  float T[3];       // per-channel throughput factor of the bounce, BSDF(indirect) * coeff (Kd/pi + Ks phong) * coeff; 0 when stopped
+  float fd[3];      // BSDF(isDirect = true) of the bounce, Kd + Ks phong
 };
 
 // renderSample + radiance, path_trace.cu:111-184.  Returns L of one pixel sample.  `trace`
@@ -1089,7 +1091,7 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
   const int nE = (int)sc.emissives.size();
   while (recur) {
     // ---- radiance() ----
-    Vertex vx{-1, -1, 0.0f, 0.0f, false};
+    Vertex vx{-1, -1, 0.0f, 0.0f, false, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
     Hit isect = sc.closest_hit(ray);
     cnt->ext_rays++;
     recur = false;
@@ -1112,6 +1114,7 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
           for (int i = 0; i < 3; i++) L_d[i] = f[i] * (t_emm.mat.ke[i] * g);
           vx.light = ls.light_tri;
           vx.g = g;
+          for (int i = 0; i < 3; i++) vx.fd[i] = f[i];
         }
       }
       // Russian roulette + continuation, path_trace.cu:130-141
@@ -1126,7 +1129,8 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
         float cosn = dot(nextDir, shading_normal(tri, isect.point));
         float coeff = isSpecular ? (cosn / p_sample) / P.p_rr : cosn * c_diff;
         for (int i = 0; i < 3; i++) mult[i] = (mult[i] * f[i]) * coeff;
-        vx.b = coeff / kPi;   // bookkeeping for the adjoint only (diffuse materials)
+        vx.b = coeff / kPi;   // d(throughput factor)/dKd: the diffuse part of the BSDF is Kd/pi with or without a Phong lobe
+        for (int i = 0; i < 3; i++) vx.T[i] = f[i] * coeff;
         vx.cont = true;
         ray.p = isect.point;
         ray.d = nextDir;
@@ -1440,7 +1444,7 @@ void orc_create_graph(void* h, const OrcParams* p, const uint8_t* target, double
 //   loss = sum over rows [row_begin,row_end) of (y-y*)^2 / (3*W*H)
 //   grad[t][c] = sum_pixels dloss/dL_c * (1/spp) * sum_samples dL_sample,c/dKd[t][c]
 // The estimator is polynomial in Kd and the sampling does not depend on Kd, so the gradient of the
-// estimator is exact (valid for Ks == 0 materials).  Accumulated in double here.
+// estimator is exact, with or without a Phong lobe (the recorded per-channel factors T_k, fd_k carry it).  Accumulated in double here.
 void orc_render_grad(void* h, const OrcParams* p, const uint8_t* target, double* loss_out, double* grad, float* img, int threads) {
   Scene* sc = (Scene*)h;
   Params P = to_params(p);
@@ -1467,7 +1471,8 @@ void orc_render_grad(void* h, const OrcParams* p, const uint8_t* target, double*
         float Ls[3];
         tr.clear();
         render_sample(*sc, P, r, c, s, Ls, &cnt, &tr);
-        // L = sum_k P_k (E + D'_k);  P_{k+1} = P_k Kd_k b_k;  D_k = Kd_k Ke_l g_k; on a miss D' = D_{k-1}.
+        // L = sum_k P_k (E + D'_k);  P_{k+1} = P_k T_k, T_k = (Kd_k/pi + Ks phong) coeff_k;  D_k = (Kd_k + Ks phong) Ke_l g_k;
+        // on a miss D' = D_{k-1}.  dT_k/dKd = coeff_k/pi = b_k and dD_k/dKd = Ke_l g_k whatever the Phong term is.
         int K = (int)tr.size();
         for (int ch = 0; ch < 3; ch++) {
           std::vector<double> Pk(K + 1, 0.0), C(K, 0.0);
@@ -1476,12 +1481,12 @@ void orc_render_grad(void* h, const OrcParams* p, const uint8_t* target, double*
           double Dprev = 0.0;
           for (int k = 0; k < K; k++) {
             double D = Dprev;
-            if (tr[k].tri >= 0) D = (tr[k].light >= 0) ? (double)sc->tri(tr[k].tri).mat.kd[ch] * ((double)sc->tri(tr[k].light).mat.ke[ch] * (double)tr[k].g) : 0.0;
+            if (tr[k].tri >= 0) D = (tr[k].light >= 0) ? (double)tr[k].fd[ch] * ((double)sc->tri(tr[k].light).mat.ke[ch] * (double)tr[k].g) : 0.0;
             C[k] = E + D;
             Dprev = D;
-            Pk[k + 1] = (tr[k].tri >= 0 && tr[k].cont) ? Pk[k] * (double)sc->tri(tr[k].tri).mat.kd[ch] * (double)tr[k].b : 0.0;
+            Pk[k + 1] = (tr[k].tri >= 0 && tr[k].cont) ? Pk[k] * (double)tr[k].T[ch] : 0.0;
           }
-          // adjoint sweep: Pbar_k = C_k + Kd_k b_k Pbar_{k+1}
+          // adjoint sweep: Pbar_k = C_k + T_k Pbar_{k+1}
           double Pbar_next = 0.0;
           for (int k = K - 1; k >= 0; k--) {
             int t = tr[k].tri;
@@ -1490,7 +1495,7 @@ void orc_render_grad(void* h, const OrcParams* p, const uint8_t* target, double*
               double gk = Pk[k] * dC;
               if (tr[k].cont) gk += Pk[k] * (double)tr[k].b * Pbar_next;
               gpart[tid][(size_t)t * 3 + ch] += dLdpx[ch] * gk;
-              Pbar_next = C[k] + (tr[k].cont ? (double)sc->tri(t).mat.kd[ch] * (double)tr[k].b * Pbar_next : 0.0);
+              Pbar_next = C[k] + (tr[k].cont ? (double)tr[k].T[ch] * Pbar_next : 0.0);
             } else {
               // miss: the stale D_{k-1} is re-added with P_k -> gradient flows to triangle t_{k-1}
               if (k > 0 && tr[k - 1].tri >= 0 && tr[k - 1].light >= 0) {

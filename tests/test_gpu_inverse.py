@@ -125,3 +125,36 @@ def test_inverse_recovers_reference_materials(ipt):
         assert err.mean() < 0.01 and err.max() < 0.03, (name, float(err.mean()), float(err.max()))
     opt.close()
     sc.close()
+
+
+def test_gcn_pipeline_end_to_end(ipt, tmp_path):
+    """The reference's learning pipeline on this library (ipt.py:69-140): createGraph data product for a few scenes on
+    the device (TorchScene.graph_data), DGL-free GCN (gcn.build_graph / gcn.fit), prediction rendered back with
+    setMaterials + forward pass (render_with_materials).  The loss must drop and the predicted image must render."""
+    import torch
+    from inverse_path_tracer_b200 import gcn
+    from inverse_path_tracer_b200.ipt_cuda import parse_scene_file
+    from inverse_path_tracer_b200.torch_api import TorchScene
+    data, scenes = [], []
+    for i in range(4):
+        sc = TorchScene(parse_scene_file(os.path.join(ASSETS, "scenes", "%d.txt" % i)), asset_root=ASSETS)
+        labels = sc.scene.get_materials().copy()
+        tgt = torch.empty((100, 100, 3), dtype=torch.uint8, device="cuda")
+        sc.render(ipt.default_params(width=100, height=100, spp=64, seed=i), out_u8=tgt)
+        w, pixel, light = sc.graph_data(ipt.default_params(width=100, height=100, spp=64, seed=100 + i), tgt)
+        assert w.shape == (sc.nT + 1, sc.nT) and not torch.isnan(pixel).any()
+        data.append((w, pixel, light, labels))
+        scenes.append(sc)
+    _, l_short = gcn.fit(data, epochs=1, lr=1e-3, device="cuda")
+    model, l_long = gcn.fit(data, epochs=300, lr=1e-3, device="cuda")
+    assert l_long < 0.8 * l_short, (l_short, l_long)
+    # render the prediction for scene 0 (ipt_cuda.render_with_materials: setMaterials + createImage)
+    W, x = gcn.build_graph(*data[0][:3])
+    pred = model(W.cuda(), x.cuda()).detach()
+    assert pred.shape == (scenes[0].nT, 3) and float(pred.min()) > 0 and float(pred.max()) < 1
+    scenes[0].set_materials(pred)
+    img = scenes[0].render(ipt.default_params(width=100, height=100, spp=32, seed=9))
+    assert torch.isfinite(img).all() and float(img.mean()) > 0.05
+    assert np.abs(scenes[0].scene.get_materials() - pred.cpu().numpy()).max() < 1e-7   # getMaterials sees the device-side set
+    for sc in scenes:
+        sc.close()

@@ -379,6 +379,29 @@ def test_gpu_bvh_builder_degenerate_and_scene_inputs(ipt, oracle):
         assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1]) and a[0].tobytes() == b[0].tobytes()
 
 
+def test_grad_parity_with_phong_lobe(ipt, oracle):
+    """the adjoint on a scene with Ks != 0 (Cornell box + loader-fuzz mesh with specular materials and vertex normals):
+    loss equal, gradient within 1e-3 of the oracle's double-precision adjoint, which tests/test_oracle.py holds to
+    central finite differences on the same kind of scene; both integrator templates (brute force and BVH)"""
+    objs = [{"pos": [0, 0, 5], "ori": [0.1, 0.2, 0.3], "scl": [1, 1, 1], "obj": "./fuzz/case_18.obj", "mtl": "./fuzz/case_18.mtl"}] + scene_objects("cornell")
+    o = oracle.OracleScene(objs, ASSETS)
+    assert np.abs(o.triangle_table()["ks"]).max() > 0.5
+    rng = np.random.RandomState(6)
+    kd = rng.uniform(0.2, 0.8, (o.nT, 3)).astype(np.float32)
+    o.set_materials(kd)
+    w, h, spp = 24, 24, 16
+    target = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    loss_o, grad_o, img_o = o.render_grad(oracle.make_params(w, h, spp, seed=3, max_depth=64), target, threads=oracle.hardware_threads())
+    for mode in (0, 2):
+        g = ipt.Scene(objs, asset_root=ASSETS, traversal_mode=mode)
+        g.set_materials(kd)
+        loss_g, grad_g, img_g = g.render_grad(ipt.default_params(width=w, height=h, spp=spp, seed=3, max_depth=64), target)
+        assert img_g.tobytes() == img_o.tobytes(), mode
+        assert abs(loss_g - loss_o) <= 1e-9 * abs(loss_o)
+        assert np.abs(grad_g - grad_o).max() <= 1e-3 * np.abs(grad_o).max(), (mode, float(np.abs(grad_g - grad_o).max()), float(np.abs(grad_o).max()))
+        g.close()
+
+
 def test_torch_front_end_and_autograd(ipt, oracle):
     """device-pointer entry points through torch tensors on torch's current stream; RenderLoss backward = path adjoint"""
     import torch
