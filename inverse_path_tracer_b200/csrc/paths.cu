@@ -50,7 +50,8 @@ __device__ __forceinline__ int adj_light(const AdjVertex& v) { return __float_as
 // ~2.4 trips at ~22 lanes) and taking a ray is one 16-byte load.  Entry = {direction, work item}; the generator's own
 // cursor (pixel, row / column, next sample, end) lives in two more shared-memory slots of the lane.
 constexpr int kRing = 4;
-constexpr int kRingF4 = kRing + 2;
+constexpr int kRingF4 = kRing + 3;   // + two generator slots + the lane's item slot {partial sum rgb, work item}
+constexpr int kRingWords = kRingF4 * 4 + 1;   // 32-bit words per thread: the float4 slots + one word (last claim position)
 constexpr uint32_t kRingStride = kBlock * 16u;   // bytes between two slots of one thread
 // BVH is a compile-time flag: in brute-force mode every scene access is a shared-memory access with 32-bit
 // addressing (a runtime choice between shared and global pointers forces generic loads)
@@ -80,15 +81,21 @@ constexpr int kSweepPerTrip = IPT_SWEEP_PER_TRIP;   // adjoint sweep: at most th
 #define IPT_SWEEP_QUORUM 1
 #endif
 constexpr int kSweepQuorum = IPT_SWEEP_QUORUM;      // ... while at least this many lanes of the warp have one pending
+// resident blocks per SM: the forward and graph kernels of plain brute-force scenes -- every scene the reference ships --
+// fit 80 registers without spills once the per-item state lives in shared memory, i.e. six blocks (24 warps) per SM
+// instead of five; the adjoint and the BVH / Phong / vertex-normal variants would spill there and keep five
+#ifndef IPT_MINB_FAST
+#define IPT_MINB_FAST 6
+#endif
 template <int MODE, bool BVH, bool PLAIN>
-__global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRender rp, DevOut out) {
+__global__ void __launch_bounds__(kBlock, (MODE != MODE_GRAD && !BVH && PLAIN) ? IPT_MINB_FAST : IPT_MINB) k_paths(DevScene sc, DevRender rp, DevOut out) {
   extern __shared__ float4 smem[];
   const int nT = sc.nT, nE = sc.nE;
   SmallScene ss;
   ss.nGroups = 0;
   // per-thread camera-ray ring + generator state (see [B]): kRingF4 float4 columns, slot k of thread t at [k * kBlock + t]
   const uint32_t ring_a = smem_addr(smem) + threadIdx.x * 16u;
-  float4* cursor = smem + kRingF4 * kBlock;
+  float4* cursor = smem + kRingF4 * kBlock + kBlock / 4;   // float4 slots + one 32-bit word per thread
   int* bvh_stack = reinterpret_cast<int*>(cursor);
   if (BVH) cursor += (sc.bvh_depth * kBlock + 3) / 4;   // one stack column per thread, as deep as the tree
   // brute-force set: the whole scene, or in BVH mode the large triangles kept out of the tree
@@ -121,16 +128,19 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   const f3 zero3 = mk3(0.0f, 0.0f, 0.0f);
 
   // ---- work item bookkeeping -------------------------------------------------------------------
-  unsigned item = 0xffffffffu;    // work item (pixel, sample group) whose samples this lane is tracing
-  int pixel = 0;                  // its global pixel index (RNG counter, target lookup)
+  // the lane's work item (pixel, sample group) and the running sum of its finalised samples live in shared memory (slot
+  // kRing + 2 = {part r, g, b, item}): they are touched once per path, not once per trip, and registers decide occupancy
+  const uint32_t item_a = ring_a + (kRing + 2) * kRingStride;
+  sts4(item_a, make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0xffffffffu)));
+  int pixel = 0;                  // global pixel index of the item (RNG counter, target lookup)
   int fin_left = 0;               // samples of the item not yet finalised
   int cur_s = 0;                  // sample index of the path in flight (RNG counter)
-  float part0 = 0.0f, part1 = 0.0f, part2 = 0.0f;
   int rhead = 0, rcount = 0;      // camera-ray ring: first entry, entries
   bool g_done = false;            // the generator found the work queue empty
   sts4(ring_a + (kRing + 1) * kRingStride, make_float4(0.0f, 0.0f, 0.0f, 0.0f));   // generator cursor {next sample, end sample, next item, end of the claimed run}: all "used up"
-  unsigned claim_base = 0;        // queue position this warp saw at its last claim (sizes the next one)
-  const unsigned claim_div = gridDim.x * blockDim.x * 2u;
+  // queue position this lane saw at its last claim (sizes the next one): one more shared-memory word per thread, behind the float4 slots
+  const uint32_t claim_a = smem_addr(smem) + kRingF4 * kRingStride + threadIdx.x * 4u;
+  sts1i(claim_a, 0);
   // floor(i / groups) and floor(pixel / width) by multiplication with ceil(2^64 / d) (exact below 2^32)
   auto decode_item = [&](unsigned my, int& pix_local, int& g, int& px, int& r, int& c) {
     pix_local = rp.groups == 1 ? (int)my : (int)__umul64hi((unsigned long long)my, rp.magic_groups);
@@ -170,7 +180,7 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   float sw0 = 0.0f, sw1 = 0.0f, sw2 = 0.0f;  // its pixel's dLoss/dL / spp
   float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;     // dLoss/dL_pixel / spp of the item's pixel
   int path_len = 0;                          // vertices recorded for the path being finalised
-  unsigned n_paths = 0, n_ext = 0, n_shadow = 0;   // per lane and launch: < 2^32 (a lane traces ~10^5 rays per second of launch)
+  unsigned n_ext = 0, n_shadow = 0;   // per lane and launch: < 2^32 (a lane traces ~10^5 rays per second of launch); paths = n_pix * spp, counted by lane 0 of block 0
   // the light connection of the current bounce; written in [A] and read in [C] / [D] only when sh_valid, so they are
   // not reset per trip (the resets were ~30 register moves per trip at full warp width)
   f3 sh_org = zero3, sh_dir = zero3;
@@ -257,7 +267,11 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
 
   // finalise one sample: toneMap's running sum of src[i]/SPP (path_trace.cu:190-193) / park the adjoint sweep
   auto finalize = [&]() {
-    if (MODE == MODE_RENDER) { part0 += L0 * rp.inv_spp; part1 += L1 * rp.inv_spp; part2 += L2 * rp.inv_spp; }
+    float4 part = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (MODE == MODE_RENDER) {
+      part = lds4(item_a);
+      part.x += L0 * rp.inv_spp; part.y += L1 * rp.inv_spp; part.z += L2 * rp.inv_spp;
+    }
     if (MODE == MODE_GRAD) {
       // the previous path's sweep has not caught up (this path was shorter): finishing it here would run the sweep with
       // one or two lanes of the warp (measured: 22 % of the sweep steps, half of the sweep's instructions), so the lane
@@ -270,10 +284,12 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       sw0 = w0; sw1 = w1; sw2 = w2;
     }
     fin_left--;
-    if (fin_left == 0) {
-      if (MODE == MODE_RENDER) {
-        float* dst = out.partial + (size_t)item * 3;
-        dst[0] = part0; dst[1] = part1; dst[2] = part2;
+    if (MODE == MODE_RENDER) {
+      if (fin_left == 0) {
+        float* dst = out.partial + (size_t)__float_as_uint(part.w) * 3;
+        dst[0] = part.x; dst[1] = part.y; dst[2] = part.z;
+      } else {
+        sts4(item_a, part);
       }
     }
   };
@@ -298,13 +314,14 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
     if (fm) {
       // guided self-scheduling: a claim is a run of n consecutive items per lane, n shrinking from 8 to 1 as the queue
       // empties (few atomics while there is plenty of work, single items at the end so the launch does not end in a tail)
-      const unsigned remaining = n_items > claim_base ? n_items - claim_base : 0u;
-      const unsigned n = min(max(remaining / claim_div, 1u), 8u);
       const int leader = __ffs(fm) - 1;
+      const unsigned claim_base = (unsigned)__shfl_sync(kFull, lds1i(claim_a), leader);   // warp-uniform n: the leader's view
+      const unsigned remaining = n_items > claim_base ? n_items - claim_base : 0u;
+      const unsigned n = min(max(remaining / (gridDim.x * blockDim.x * 2u), 1u), 8u);
       unsigned base = 0;
       if ((int)lane == leader) base = atomicAdd(out.work_counter, (unsigned)__popc(fm) * n);   // overshoot <= 8 per lane: no wrap (make_plan)
       base = __shfl_sync(kFull, base, leader);
-      claim_base = base;
+      sts1i(claim_a, (int)base);
       if (claim) {
         it_next = base + (unsigned)__popc(fm & ((1u << lane) - 1u)) * n;
         it_end = min(it_next + n, n_items);
@@ -505,15 +522,14 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
       if (want && rcount > 0) {
         const float4 e = lds4(ring_a + (uint32_t)rhead * kRingStride);
         const unsigned e_item = __float_as_uint(e.w);
-        const bool new_item = e_item != item;
+        const bool new_item = e_item != (unsigned)lds1i(item_a + 12u);
         if (!new_item || (fin_left == 0 && !end_after)) {
           if (new_item) {
             int pix_local, g, r, c;
             decode_item(e_item, pix_local, g, pixel, r, c);
-            item = e_item;
+            sts4(item_a, make_float4(0.0f, 0.0f, 0.0f, e.w));
             cur_s = g * rp.group_samples - 1;
             fin_left = min(rp.spp, (g + 1) * rp.group_samples) - g * rp.group_samples;
-            part0 = part1 = part2 = 0.0f;
             if (MODE != MODE_RENDER) {
               const unsigned char* tp = out.target + (size_t)pixel * 3;
               pix0 = (float)tp[0] / 255.0f; pix1 = (float)tp[1] / 255.0f; pix2 = (float)tp[2] / 255.0f;   // inv_scene.h:74-77
@@ -534,7 +550,6 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
           gdst = nT;
           if (!end_after) { q0 = q1 = q2 = 1.0f; L0 = L1 = L2 = 0.0f; e_tri = -1; d0 = d1 = d2 = 0.0f; }
           ext_valid = true;
-          n_paths++;
         }
       }
     }
@@ -629,7 +644,9 @@ __global__ void __launch_bounds__(kBlock, IPT_MINB) k_paths(DevScene sc, DevRend
   }
 
   // ---- epilogue: counters + per-block accumulators --------------------------------------------------
-  unsigned long long w_paths = n_paths, w_ext = n_ext, w_shadow = n_shadow;
+  // every work item is traced to the end, so the launch traced exactly n_pix * spp paths
+  unsigned long long w_paths = (blockIdx.x == 0 && threadIdx.x == 0) ? (unsigned long long)rp.n_pix * (unsigned long long)rp.spp : 0ull;
+  unsigned long long w_ext = n_ext, w_shadow = n_shadow;
   for (int o = 16; o > 0; o >>= 1) {
     w_paths += __shfl_down_sync(kFull, w_paths, o);
     w_ext += __shfl_down_sync(kFull, w_ext, o);
@@ -767,7 +784,7 @@ __global__ void k_set_kd(float4* __restrict__ mat, const float* __restrict__ kd,
 // ------------------------------------------------------------------------------------------------
 
 size_t paths_smem_bytes(const DevScene& sc, int acc_floats) {
-  size_t b = (size_t)acc_floats * sizeof(float) + (size_t)kRingF4 * kBlock * sizeof(float4);   // accumulators + camera-ray rings
+  size_t b = (size_t)acc_floats * sizeof(float) + (size_t)kRingWords * kBlock * sizeof(float);   // accumulators + camera-ray rings
   if (!sc.use_bvh || sc.nE <= kLightSmemMax) b += (size_t)3 * sc.nE * sizeof(float4);
   if (!sc.use_bvh) b += small_scene_smem_bytes(sc.nStream) + (size_t)kMatStride * sc.nT * sizeof(float4);
   else b += bvh_stack_bytes(sc) + (sc.nGroups > 0 ? small_scene_smem_bytes(sc.nStream) : 0);
