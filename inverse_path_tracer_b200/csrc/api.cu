@@ -364,9 +364,16 @@ int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan) {
   rp.n_pix = rows * p->width;
   // work-item index -> (pixel, group) and pixel -> (row, column) by multiplication (an integer division per item is a
   // visible cost when items are small)
-  auto magic = [](unsigned d) { return d > 1 ? ~0ull / d + 1 : 0ull; };   // ceil(2^64 / d) for d that is not a power of two; exact use below
-  rp.magic_groups = magic((unsigned)rp.groups);
-  rp.magic_width = magic((unsigned)p->width);
+  auto magic = [](unsigned d, unsigned* m, int* shift) {   // device_scene.h: floor(x / d) = umulhi(x, m) >> shift for x < 2^31
+    *m = 0; *shift = 0;
+    if (d < 2) return;
+    int l = 0;
+    while ((1ull << l) < d) l++;
+    *m = (unsigned)(((1ull << (31 + l)) / d) + 1ull);
+    *shift = l - 1;
+  };
+  magic((unsigned)rp.groups, &rp.magic_groups, &rp.shift_groups);
+  magic((unsigned)p->width, &rp.magic_width, &rp.shift_width);
   plan->rows = rows;
   return 0;
 }

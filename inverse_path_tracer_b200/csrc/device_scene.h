@@ -62,7 +62,10 @@ struct DevRender {
   int row_begin;        // first image row of this shard
   int row_step;         // the shard owns rows row_begin, row_begin + row_step, ... (interleaved sharding)
   int n_pix;            // pixels in this shard (compact local index = local_row * width + column)
-  unsigned long long magic_groups, magic_width;   // ceil(2^64 / d): floor(x / d) = __umul64hi(x, magic) for x < 2^32, d > 1
+  // floor(x / d) for x < 2^31 and d >= 2 as (__umulhi(x, magic) >> shift), magic = floor(2^(31 + l) / d) + 1, shift = l - 1,
+  // l = ceil(log2 d) (a 32-bit magic number is exact for 31-bit dividends); d == 1 is handled by the caller
+  unsigned magic_groups, magic_width;
+  int shift_groups, shift_width;
 };
 
 // counters[0..2] = paths, extension rays, shadow rays

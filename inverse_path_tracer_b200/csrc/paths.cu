@@ -141,11 +141,11 @@ __global__ void __launch_bounds__(kBlock, (MODE != MODE_GRAD && !BVH && PLAIN) ?
   // queue position this lane saw at its last claim (sizes the next one): one more shared-memory word per thread, behind the float4 slots
   const uint32_t claim_a = smem_addr(smem) + kRingF4 * kRingStride + threadIdx.x * 4u;
   sts1i(claim_a, 0);
-  // floor(i / groups) and floor(pixel / width) by multiplication with ceil(2^64 / d) (exact below 2^32)
+  // floor(i / groups) and floor(pixel / width) by multiplication (device_scene.h: exact for 31-bit dividends)
   auto decode_item = [&](unsigned my, int& pix_local, int& g, int& px, int& r, int& c) {
-    pix_local = rp.groups == 1 ? (int)my : (int)__umul64hi((unsigned long long)my, rp.magic_groups);
+    pix_local = rp.groups == 1 ? (int)my : (int)(__umulhi(my, rp.magic_groups) >> rp.shift_groups);
     g = (int)(my - (unsigned)pix_local * (unsigned)rp.groups);
-    const int lr = rp.width == 1 ? pix_local : (int)__umul64hi((unsigned long long)pix_local, rp.magic_width);
+    const int lr = rp.width == 1 ? pix_local : (int)(__umulhi((unsigned)pix_local, rp.magic_width) >> rp.shift_width);
     c = pix_local - lr * rp.width;
     r = rp.row_begin + lr * rp.row_step;       // interleaved row shards
     px = r * rp.width + c;                     // global pixel index
