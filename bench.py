@@ -519,6 +519,16 @@ def config5_extra(args, ipt, native, torch, np, dev, peaks, peak_kind):
             best = (ms, cnt)
     out["path_tracing_1024x1024_16spp_depth8"] = {"integrator": "wavefront", "ms_per_frame": best[0], "mrays_per_s": (best[1]["ext_rays"] + best[1]["shadow_rays"]) / best[0] / 1e3,
                                                   "mpaths_per_s": best[1]["paths"] / best[0] / 1e3}
+    # adjoint replay of the same frame through the wavefront (vertex record + backward sweep), depth 8
+    tgt = np.random.RandomState(1).randint(0, 256, (1024, 1024, 3)).astype(np.uint8)
+    sc.render_grad(p(60), tgt)
+    best_adj = None
+    for i in range(2):
+        sc.render_grad(p(i), tgt)
+        km = sc.kernel_times_ms(2)      # newest first: adjoint replay, forward pass
+        if best_adj is None or km[0] < best_adj[0]:
+            best_adj = (float(km[0]), float(km[1]))
+    out["adjoint_1024x1024_16spp_depth8"] = {"integrator": "wavefront (recorded vertices, k_wf_sweep)", "adjoint_ms": best_adj[0], "forward_ms": best_adj[1]}
     # incoherent closest hit: random origins inside the room, random directions
     rng = np.random.RandomState(0)
     n = 8_000_000

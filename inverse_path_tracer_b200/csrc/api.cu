@@ -549,6 +549,35 @@ int launch_grad_pass(SceneHandle* h, const Plan& plan, const unsigned char* targ
   const DevScene sc = h->dev();
   const int nT = sc.nT;
   if (nT == 0) return 0;
+  if (sc.use_bvh && h->integrator != 1) {
+    // BVH scenes: the adjoint replays the paths through the wavefront integrator with vertex recording and sweeps every
+    // batch backwards (wavefront.cu, k_wf_sweep); the record bounds the batch (vdepth x cap x 32 or 64 bytes)
+    const DevRender& rp = plan.rp;
+    const int vf4 = sc.plain ? 2 : 4;
+    const long long total = (long long)rp.n_pix * rp.spp;
+    const long long rec_budget = (long long)6 << 30;   // bytes of vertex record per batch
+    long long cap_ll = std::min<long long>(std::min<long long>(total, (long long)h->wf_slots), rec_budget / ((long long)rp.max_depth * vf4 * 16));
+    const int cap = (int)std::max<long long>(1, cap_ll);
+    IPT_CUDA(h->wavefront.reserve(wavefront_workspace_bytes(cap)));
+    IPT_CUDA(h->vstacks.reserve(wavefront_record_bytes(cap, rp.max_depth, vf4)));
+    IPT_CUDA(h->counters.reserve(16 * sizeof(unsigned long long)));
+    if (!h->host_live) IPT_CUDA(cudaHostAlloc((void**)&h->host_live, sizeof(int), cudaHostAllocDefault));
+    unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
+    IPT_CUDA(cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned long long), st));
+    WavefrontAdjoint adj;
+    adj.record = h->vstacks.ptr;
+    adj.vdepth = rp.max_depth;
+    adj.dldpx = (const float*)h->dldpx.ptr;
+    adj.grad = lossgrad_dev + 1;
+    const int slot = (int)(h->ev_count % SceneHandle::kEventRing);
+    IPT_CUDA(cudaEventRecord(h->ev_start[slot], st));
+    unsigned long long launches = 0;
+    IPT_CUDA(launch_wavefront(sc, rp, h->wavefront.ptr, cap, nullptr, ctr, h->sm_count, h->host_live, &launches, st, &adj));
+    IPT_CUDA(cudaEventRecord(h->ev_stop[slot], st));
+    h->ev_count++;
+    g_launches += launches;
+    return 0;
+  }
   const int k = pick_chunks(h, plan);
   GradLaunch g;
   if (prepare_grad(h, plan, k, &g) != 0) return -1;

@@ -224,9 +224,26 @@ static int enqueue_step(InverseHandle* o, unsigned long long seed) {
   const DevRender& rp = plan.rp;
   const DevScene sc = h->dev();
   const size_t n3 = (size_t)rp.n_pix * 3;
+  IPT_CUDA(h->dldpx.reserve(n3 * sizeof(float)));
+  if (sc.use_bvh && h->integrator != 1) {
+    // BVH scenes: forward pass and adjoint replay both run through the wavefront integrator (api.cu)
+    IPT_CUDA(cudaMemsetAsync(o->st.lossgrad, 0, (size_t)o->n * sizeof(double), st));
+    if (launch_forward(h, plan, nullptr, nullptr, nullptr, st, /*resolve=*/false) != 0) return -1;
+    const double inv_n_w = 1.0 / (3.0 * (double)rp.width * (double)rp.height);
+    k_resolve_loss<<<(rp.n_pix + 255) / 256, 256, 0, st>>>((const float*)h->partial.ptr, rp.n_pix, rp.groups, o->target_dev, rp.row_begin, rp.row_step, rp.width,
+                                                           inv_n_w, 1.0f / (float)rp.spp, nullptr, (float*)h->dldpx.ptr, o->st.lossgrad);
+    IPT_CUDA(cudaGetLastError());
+    g_launches += 1;
+    if (launch_grad_pass(h, plan, o->target_dev, o->st.lossgrad, st) != 0) return -1;
+    k_inverse_update<<<1, 256, 0, st>>>(o->st, o->peers, o->cfg.rank, o->cfg.world, o->nT, h->mat, o->cfg.lr, o->cfg.beta1, o->cfg.beta2, o->cfg.eps,
+                                       o->cfg.kd_min, o->cfg.kd_max, kHistoryCap, (unsigned long long)(o->cfg.timeout_ms > 0 ? o->cfg.timeout_ms : 10000) * 1000000ull);
+    IPT_CUDA(cudaGetLastError());
+    g_launches += 1;
+    o->steps_issued++;
+    return 0;
+  }
   const int k = pick_chunks(h, plan);
   GradLaunch g;
-  IPT_CUDA(h->dldpx.reserve(n3 * sizeof(float)));
   if (prepare_forward(h, plan) != 0 || prepare_grad(h, plan, k, &g) != 0) return -1;
   unsigned long long* ctr = (unsigned long long*)h->counters.ptr;
   IPT_CUDA(cudaMemsetAsync(o->st.lossgrad, 0, (size_t)o->n * sizeof(double), st));

@@ -18,8 +18,18 @@ cudaError_t launch_paths(int mode, const DevScene& sc, const DevRender& rp, cons
 // wavefront forward pass for BVH scenes: batches of <= cap paths, state in `workspace`; adds into `partial` exactly
 // what k_paths<RENDER> would write.  host_live: one pinned int (used only with unbounded depth).
 size_t wavefront_workspace_bytes(int cap);
+// adjoint replay through the wavefront (BVH scenes): `record` holds wavefront_record_bytes(cap, vdepth, vf4) bytes (vf4 = 2
+// for plain scenes, 4 otherwise); every batch is replayed with vertex recording and swept backwards into grad[3 nT] (doubles,
+// atomics), weighted by dldpx (shard-local pixels).  With `adj` the pass writes no partial sums.
+struct WavefrontAdjoint {
+  void* record;
+  int vdepth;
+  const float* dldpx;
+  double* grad;
+};
+size_t wavefront_record_bytes(int cap, int vdepth, int vf4);
 cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* workspace, int cap, float* partial, unsigned long long* counters,
-                             int sm_count, int* host_live, unsigned long long* n_launches, cudaStream_t st);
+                             int sm_count, int* host_live, unsigned long long* n_launches, cudaStream_t st, const WavefrontAdjoint* adj = nullptr);
 // one bounce of the wavefront integrator (trace.cu): closest hits of the rays [0, n) u [cap, cap + n), n = *n_live
 cudaError_t launch_trace_bounce(const DevScene& sc, const float* rays, const int* n_live, int cap, int* tri, float* t, unsigned long long* counter,
                                 int sm_count, unsigned long long* n_launches, cudaStream_t st);

@@ -34,6 +34,16 @@ enum { WF_END_AFTER = 1, WF_SH_VALID = 2, WF_EXT_VALID = 4 };
 #endif
 constexpr int kWfBlock = IPT_WF_BLOCK;
 
+// Adjoint recording (wavefront form of k_paths<GRAD>): the replay of a batch writes one vertex per
+// (bounce, path) -- V[(bounce * cap + path) * vf4 ..], vf4 = 2 float4 for plain scenes ({tri, b, light, g} {P}), 4 with a
+// Phong lobe / vertex normals (+ {T} {BSDF direct}) -- and the number of vertices of every path; k_wf_sweep then runs
+// Pbar_k = C_k + T_k Pbar_{k+1} backwards over each path.  V == nullptr: plain forward pass.
+struct WfRecord {
+  float4* V;
+  int* vlen;
+  int vf4;
+};
+
 struct WfBatch {
   int cap;          // slots per array
   int tile_p0;      // first local pixel of the tile
@@ -100,10 +110,11 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(DevScene sc, DevRender
 __global__ void __launch_bounds__(kWfBlock, IPT_WF_MINB) k_wf_shade(DevScene sc, DevRender rp, WfBatch b, int bounce, const float4* __restrict__ sin_, float4* __restrict__ sout,
                                                        const float* __restrict__ rin, float* __restrict__ rout, const int* __restrict__ hit_tri,
                                                        const float* __restrict__ hit_t, const int* __restrict__ n_in, int* __restrict__ n_out,
-                                                       float* __restrict__ lsamp, unsigned long long* __restrict__ counters) {
+                                                       float* __restrict__ lsamp, unsigned long long* __restrict__ counters, WfRecord rec) {
   const int nT = sc.nT, nE = sc.nE;
   const size_t cap = (size_t)b.cap;
   const int n = *n_in;
+  const bool RECORD = rec.V != nullptr;
   const bool PLAIN = sc.plain != 0;
   const float4* __restrict__ mat = sc.mat;
   const float4* __restrict__ slight = sc.light;
@@ -147,11 +158,15 @@ __global__ void __launch_bounds__(kWfBlock, IPT_WF_MINB) k_wf_shade(DevScene sc,
           if (!(cos_tp < 0.0f) && hs_tri == sh_light) {
             const float g = (sh_cos * cos_tp) / ((hs_t * hs_t) * sh_pt);
             d0 = f0 * (lmb.x * g); d1 = f1 * (lmb.y * g); d2 = f2 * (lmb.z * g);
+            if (RECORD) {   // the connection of the vertex recorded one bounce ago is visible
+              float* va = reinterpret_cast<float*>(rec.V + ((size_t)(bounce - 1) * cap + path) * rec.vf4);
+              *reinterpret_cast<float2*>(va + 2) = make_float2(__int_as_float(sh_light), g);
+            }
           }
         }
         L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2);
         q0 = m0; q1 = m1; q2 = m2;
-        if (was_end) alive = false;
+        if (was_end) { alive = false; if (RECORD) rec.vlen[path] = bounce; }
       }
       // ---- [A] this bounce's hit (path_trace.cu:111-144) ----
       if (alive && was_ext) {
@@ -161,6 +176,12 @@ __global__ void __launch_bounds__(kWfBlock, IPT_WF_MINB) k_wf_shade(DevScene sc,
         if (tri < 0) {
           L0 = fmaf(q0, e0 + d0, L0); L1 = fmaf(q1, e1 + d1, L1); L2 = fmaf(q2, e2 + d2, L2);
           alive = false;
+          if (RECORD) {
+            float4* vp = rec.V + ((size_t)bounce * cap + path) * rec.vf4;
+            vp[0] = make_float4(__int_as_float(-1), 0.0f, __int_as_float(-1), 0.0f);
+            vp[1] = make_float4(q0, q1, q2, 0.0f);
+            rec.vlen[path] = bounce + 1;
+          }
         } else {
           int pixel, cur_s;
           float pix_c, pix_r;
@@ -171,6 +192,7 @@ __global__ void __launch_bounds__(kWfBlock, IPT_WF_MINB) k_wf_shade(DevScene sc,
           const f3 hit = mk3(fmaf(rdir.x, ht, rpos.x), fmaf(rdir.y, ht, rpos.y), fmaf(rdir.z, ht, rpos.z));
           const f3 ns = PLAIN ? face_n : shading_normal(sc, tri, flags, face_n, hit);
           if (bounce == 0) { e0 = mb.x; e1 = mb.y; e2 = mb.z; }
+          float vb = 0.0f, vt0 = 0.0f, vt1 = 0.0f, vt2 = 0.0f;   // adjoint record: d(throughput factor)/dKd, per-channel throughput factor
           const u4 rn = philox4x32_10((uint32_t)pixel, (uint32_t)cur_s, (uint32_t)bounce, IPT_STREAM_BOUNCE, rp.keys);
           if (nE > 0) {
             const float u_pick = u16(rn.x >> 16), r1 = u16(rn.y >> 16), r2 = u16(rn.y & 0xffffu);
@@ -230,8 +252,17 @@ __global__ void __launch_bounds__(kWfBlock, IPT_WF_MINB) k_wf_shade(DevScene sc,
             rpos = hit;
             rdir = nd;
             ext_valid = true;
+            vb = coeff / IPT_PI_F;
+            vt0 = i0 * coeff; vt1 = i1 * coeff; vt2 = i2 * coeff;
           } else {
             end_after = true;
+          }
+          if (RECORD) {
+            float4* vp = rec.V + ((size_t)bounce * cap + path) * rec.vf4;
+            vp[0] = make_float4(__int_as_float(tri), vb, __int_as_float(-1), 0.0f);
+            vp[1] = make_float4(q0, q1, q2, 0.0f);
+            if (rec.vf4 == 4) { vp[2] = make_float4(vt0, vt1, vt2, 0.0f); vp[3] = make_float4(f0, f1, f2, 0.0f); }
+            if (!sh_valid && end_after) rec.vlen[path] = bounce + 1;
           }
           if (!sh_valid) {
             d0 = d1 = d2 = 0.0f;
@@ -307,6 +338,69 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_accumulate(const float* __restr
   }
 }
 
+// backward sweep of the adjoint over the recorded vertices of a batch (the deferred sweep of k_paths<GRAD>, one thread
+// per path; for a fixed bounce the threads of a warp read consecutive vertices):
+//   Pbar_k = (E + D_k) + T_k Pbar_{k+1},   dL/dKd[t_k] += P_k (Ke_l g_k + b_k Pbar_{k+1}),   miss: the stale D_{k-1} is re-added with P_k
+// Gradient contributions are weighted by dLoss/dL of the path's pixel (dldpx, shard-local pixel index) and added to
+// grad[3 nT] with double atomics (BVH scenes have too many triangles for per-block tiles).
+__global__ void __launch_bounds__(kWfBlock) k_wf_sweep(DevScene sc, WfBatch b, WfRecord rec, const float* __restrict__ dldpx, double* __restrict__ grad) {
+  const int n = b.tile_n * b.ns;
+  const size_t cap = (size_t)b.cap;
+  const int nT = sc.nT;
+  const float4* __restrict__ mat = sc.mat;
+  for (int path = blockIdx.x * blockDim.x + threadIdx.x; path < n; path += gridDim.x * blockDim.x) {
+    const int len = rec.vlen[path];
+    if (len <= 0) continue;
+    const int ss = path / b.tile_n;
+    const int pl = b.tile_p0 + (path - ss * b.tile_n);
+    const float w0 = dldpx[3 * (size_t)pl], w1 = dldpx[3 * (size_t)pl + 1], w2 = dldpx[3 * (size_t)pl + 2];
+    const float4 first = rec.V[(size_t)path * rec.vf4];
+    float se0 = 0.0f, se1 = 0.0f, se2 = 0.0f;   // L_e: emission of the first hit (sticky, path_trace.cu:168)
+    if (__float_as_int(first.x) >= 0) { const float4 ke = __ldg(&mat[1 * nT + __float_as_int(first.x)]); se0 = ke.x; se1 = ke.y; se2 = ke.z; }
+    float pb0 = 0.0f, pb1 = 0.0f, pb2 = 0.0f;
+    for (int k = len - 1; k >= 0; k--) {
+      const float4* vp = rec.V + ((size_t)k * cap + path) * rec.vf4;
+      const float4 va = vp[0], vP = vp[1];
+      const int vtri = __float_as_int(va.x);
+      if (vtri >= 0) {
+        const float4 kd = __ldg(&mat[vtri]);
+        const int vlight = __float_as_int(va.z);
+        const float vb = va.y, vg = va.w;
+        float k0 = 0.0f, k1 = 0.0f, k2 = 0.0f;
+        if (vlight >= 0) { const float4 lke = __ldg(&mat[1 * nT + vlight]); k0 = lke.x * vg; k1 = lke.y * vg; k2 = lke.z * vg; }
+        const float g0 = vP.x * fmaf(vb, pb0, k0), g1 = vP.y * fmaf(vb, pb1, k1), g2 = vP.z * fmaf(vb, pb2, k2);
+        double* gg = grad + 3 * (size_t)vtri;
+        atomicAdd(gg + 0, (double)(w0 * g0)); atomicAdd(gg + 1, (double)(w1 * g1)); atomicAdd(gg + 2, (double)(w2 * g2));
+        if (rec.vf4 == 2) {
+          pb0 = fmaf(kd.x * vb, pb0, se0 + kd.x * k0); pb1 = fmaf(kd.y * vb, pb1, se1 + kd.y * k1); pb2 = fmaf(kd.z * vb, pb2, se2 + kd.z * k2);
+        } else {
+          const float4 vt = vp[2], vd = vp[3];
+          pb0 = fmaf(vt.x, pb0, se0 + vd.x * k0); pb1 = fmaf(vt.y, pb1, se1 + vd.y * k1); pb2 = fmaf(vt.z, pb2, se2 + vd.z * k2);
+        }
+      } else {
+        float c0 = se0, c1 = se1, c2 = se2;
+        if (k > 0) {
+          const float4* up = rec.V + ((size_t)(k - 1) * cap + path) * rec.vf4;
+          const float4 ua = up[0];
+          const int utri = __float_as_int(ua.x), ulight = __float_as_int(ua.z);
+          if (utri >= 0 && ulight >= 0) {
+            const float4 lke = __ldg(&mat[1 * nT + ulight]);
+            const float ug = ua.w;
+            const float k0 = lke.x * ug, k1 = lke.y * ug, k2 = lke.z * ug;
+            double* gg = grad + 3 * (size_t)utri;
+            atomicAdd(gg + 0, (double)(w0 * (vP.x * k0))); atomicAdd(gg + 1, (double)(w1 * (vP.y * k1))); atomicAdd(gg + 2, (double)(w2 * (vP.z * k2)));
+            float f0, f1, f2;
+            if (rec.vf4 == 2) { const float4 kd = __ldg(&mat[utri]); f0 = kd.x; f1 = kd.y; f2 = kd.z; }
+            else { const float4 ud = up[3]; f0 = ud.x; f1 = ud.y; f2 = ud.z; }
+            c0 += f0 * k0; c1 += f1 * k1; c2 += f2 * k2;
+          }
+        }
+        pb0 = c0; pb1 = c1; pb2 = c2;
+      }
+    }
+  }
+}
+
 // ---- wavefront forward pass ------------------------------------------------------------------------------
 // workspace layout (bytes, all 256-aligned): state A, state B (6 float4 x cap each), rays A, rays B
 // (2 x 6 floats x cap each), hit ids, hit t (2 x cap each), per-sample radiance (3 x cap), control words
@@ -316,9 +410,11 @@ size_t wavefront_workspace_bytes(int cap) {
   return 2 * wf_align(6 * c * sizeof(float4)) + 2 * wf_align(12 * c * sizeof(float)) + wf_align(2 * c * sizeof(int)) + wf_align(2 * c * sizeof(float)) +
          wf_align(3 * c * sizeof(float)) + 256;
 }
+// vertex record of the adjoint replay: vdepth bounces x cap paths x vf4 float4, plus the path lengths
+size_t wavefront_record_bytes(int cap, int vdepth, int vf4) { return wf_align((size_t)vdepth * cap * vf4 * sizeof(float4)) + wf_align((size_t)cap * sizeof(int)); }
 
 cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* workspace, int cap, float* partial, unsigned long long* counters,
-                             int sm_count, int* host_live, unsigned long long* n_launches, cudaStream_t st) {
+                             int sm_count, int* host_live, unsigned long long* n_launches, cudaStream_t st, const WavefrontAdjoint* adj) {
   const size_t c = (size_t)cap;
   char* w = (char*)workspace;
   float4* state[2];
@@ -335,6 +431,12 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
 
   const int shade_grid = sm_count * 8;
   cudaError_t e = cudaSuccess;
+  WfRecord rec;
+  rec.V = nullptr; rec.vlen = nullptr; rec.vf4 = sc.plain ? 2 : 4;
+  if (adj) {
+    rec.V = (float4*)adj->record;
+    rec.vlen = (int*)((char*)adj->record + wf_align((size_t)adj->vdepth * c * rec.vf4 * sizeof(float4)));
+  }
 
   const int tile_cap = std::min(rp.n_pix, cap);
   const bool unbounded = rp.max_depth <= 0;
@@ -364,7 +466,7 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
           {
             NvtxRange r("ipt.wavefront.shade");
             k_wf_shade<<<shade_grid, kWfBlock, 0, st>>>(sc, rp, b, bounce, state[cur], state[cur ^ 1], rays[cur], rays[cur ^ 1], hit_tri, hit_t, n_live + cur,
-                                                       n_live + (cur ^ 1), lsamp, counters);
+                                                       n_live + (cur ^ 1), lsamp, counters, rec);
           }
           *n_launches += 1;
           cur ^= 1;
@@ -376,7 +478,10 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
             if (*host_live == 0) break;
           }
         }
-        {
+        if (adj) {
+          NvtxRange r("ipt.wavefront.sweep");
+          k_wf_sweep<<<std::min((n_paths + kWfBlock - 1) / kWfBlock, shade_grid), kWfBlock, 0, st>>>(sc, b, rec, adj->dldpx, adj->grad);
+        } else {
           NvtxRange r("ipt.wavefront.accumulate");
           k_wf_accumulate<<<(b.tile_n + kWfBlock - 1) / kWfBlock, kWfBlock, 0, st>>>(lsamp, b, rp.group_samples, rp.groups, rp.spp, rp.inv_spp, partial);
         }

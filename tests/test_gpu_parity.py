@@ -392,13 +392,34 @@ def test_grad_parity_with_phong_lobe(ipt, oracle):
     w, h, spp = 24, 24, 16
     target = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
     loss_o, grad_o, img_o = o.render_grad(oracle.make_params(w, h, spp, seed=3, max_depth=64), target, threads=oracle.hardware_threads())
-    for mode in (0, 2):
+    for mode, integ in ((0, 0), (2, 1), (2, 2)):   # brute force; BVH through the megakernel; BVH through the wavefront (recorded vertices + k_wf_sweep)
         g = ipt.Scene(objs, asset_root=ASSETS, traversal_mode=mode)
+        g.set_integrator(integ, 0)
         g.set_materials(kd)
         loss_g, grad_g, img_g = g.render_grad(ipt.default_params(width=w, height=h, spp=spp, seed=3, max_depth=64), target)
-        assert img_g.tobytes() == img_o.tobytes(), mode
+        assert img_g.tobytes() == img_o.tobytes(), (mode, integ)
         assert abs(loss_g - loss_o) <= 1e-9 * abs(loss_o)
-        assert np.abs(grad_g - grad_o).max() <= 1e-3 * np.abs(grad_o).max(), (mode, float(np.abs(grad_g - grad_o).max()), float(np.abs(grad_o).max()))
+        assert np.abs(grad_g - grad_o).max() <= 1e-3 * np.abs(grad_o).max(), (mode, integ, float(np.abs(grad_g - grad_o).max()), float(np.abs(grad_o).max()))
+        g.close()
+
+
+def test_wavefront_adjoint_on_bvh_scene(ipt, oracle):
+    """BVH scenes replay their paths for the adjoint through the wavefront integrator (vertex record in HBM, one backward
+    sweep per batch) instead of the persistent megakernel; both must give the oracle's loss and gradient, with the record
+    forced into several batches as well (plain scene: 32-byte vertices; vertex normals: 64-byte vertices)"""
+    for name in ("rotated_cubes", "cornell_sphere"):
+        objects = scene_objects(name)
+        o = oracle.OracleScene(objects, ASSETS)
+        rng = np.random.RandomState(3)
+        w, h, spp = 24, 20, 8
+        target = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        loss_o, grad_o, _ = o.render_grad(oracle.make_params(w, h, spp, seed=4, max_depth=64), target, threads=oracle.hardware_threads())
+        g = ipt.Scene(objects, asset_root=ASSETS, traversal_mode=2)
+        for integ, slots in ((1, 0), (2, 0), (2, 1000)):
+            g.set_integrator(integ, slots)
+            loss_g, grad_g, _ = g.render_grad(ipt.default_params(width=w, height=h, spp=spp, seed=4, max_depth=64), target)
+            assert abs(loss_g - loss_o) <= 1e-9 * abs(loss_o), (name, integ, slots)
+            assert np.abs(grad_g - grad_o).max() <= 1e-3 * np.abs(grad_o).max(), (name, integ, slots, float(np.abs(grad_g - grad_o).max()), float(np.abs(grad_o).max()))
         g.close()
 
 
