@@ -309,6 +309,48 @@ static int upload_scene(SceneHandle* h) {
       wide[4 * i + 3] = make_float4(packed[2 * r + 1].x, packed[2 * r + 1].y, packed[2 * r + 1].z, 0.0f);
     }
     if (max_depth > 64) return fail("BVH deeper than 64 levels: the traversal stack (like the reference's todo[64], bvh.h:43) cannot hold it");
+    // quantised traversal records (device_scene.h): 16 bits per coordinate on the padded root box, lower bounds rounded
+    // down and upper bounds up (checked against the float the kernel reconstructs), so a quantised box contains its
+    // float box: the closest hit is a minimum over all triangles that pass their own test, a larger box never changes it
+    std::vector<float4> quant(2 * nodes.size(), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    if (!nodes.empty()) {
+      for (int k = 0; k < 3; k++) {
+        const float lo = (&packed[0].x)[k], hi = (&packed[1].x)[k];
+        h->bvh_qoff[k] = lo;
+        h->bvh_qscale[k] = (hi > lo) ? (hi - lo) / 65535.0f * 1.0000005f : 1.0f;
+      }
+      auto qlo = [&](float v, int k) {
+        int q = (int)floorf((v - h->bvh_qoff[k]) / h->bvh_qscale[k]);
+        q = std::max(0, std::min(65535, q));
+        while (q > 0 && fmaf((float)q, h->bvh_qscale[k], h->bvh_qoff[k]) > v) q--;
+        return (unsigned)q;
+      };
+      auto qhi = [&](float v, int k) {
+        int q = (int)ceilf((v - h->bvh_qoff[k]) / h->bvh_qscale[k]);
+        q = std::max(0, std::min(65535, q));
+        while (q < 65535 && fmaf((float)q, h->bvh_qscale[k], h->bvh_qoff[k]) < v) q++;
+        return (unsigned)q;
+      };
+      auto ubits = [](unsigned v) { float f; memcpy(&f, &v, 4); return f; };
+      for (size_t i = 0; i < nodes.size(); i++) {
+        if (nodes[i].rightOffset == 0) continue;
+        const size_t ch[2] = {i + 1, i + (size_t)nodes[i].rightOffset};
+        unsigned w[6];
+        for (int c = 0; c < 2; c++) {
+          const float4 blo = packed[2 * ch[c]], bhi = packed[2 * ch[c] + 1];
+          const unsigned lx = qlo(blo.x, 0), ly = qlo(blo.y, 1), lz = qlo(blo.z, 2), hx = qhi(bhi.x, 0), hy = qhi(bhi.y, 1), hz = qhi(bhi.z, 2);
+          w[3 * c + 0] = lx | (ly << 16); w[3 * c + 1] = lz | (hx << 16); w[3 * c + 2] = hy | (hz << 16);
+        }
+        quant[2 * i] = make_float4(ubits(w[0]), ubits(w[1]), ubits(w[2]), ubits(w[3]));
+        quant[2 * i + 1] = make_float4(ubits(w[4]), ubits(w[5]), wide[4 * i + 0].w, wide[4 * i + 1].w);   // + descriptors of the left / right child
+      }
+    }
+    {
+      const char* qenv = getenv("IPT_BVH_QUANT");   // developer A/B: 0 = float records
+      h->bvh_quant = (qenv && *qenv) ? (atoi(qenv) != 0) : 1;
+    }
+    IPT_CUDA(cudaMalloc(&h->bvh_q, std::max<size_t>(quant.size(), 2) * sizeof(float4)));
+    if (!quant.empty()) IPT_CUDA(cudaMemcpy(h->bvh_q, quant.data(), quant.size() * sizeof(float4), cudaMemcpyHostToDevice));
     h->bvh_root_desc = nodes.empty() ? 0 : desc_of(0);
     h->bvh_depth = max_depth;
     h->n_nodes = (int)nodes.size();

@@ -38,7 +38,14 @@ struct DevScene {
   const float4* light;
   const float4* vtx;
   const float4* bvh_nodes;   // null in brute-force mode; canonical 32-byte nodes (root box, layout parity)
-  const float4* bvh_wide;    // 64-byte traversal records: both child boxes + child descriptors per inner node
+  const float4* bvh_wide;    // 64-byte traversal records: both child boxes + child descriptors per inner node (IPT_BVH_QUANT == 0 builds)
+  // 32-byte traversal records (default): both child boxes quantised to 16 bits per coordinate on the tree's root box,
+  // rounded outwards -- six words {lo_l.x|lo_l.y<<16, lo_l.z|hi_l.x<<16, hi_l.y|hi_l.z<<16, same for the right child} + the two
+  // child descriptors.  coordinate = bvh_qoff + q * bvh_qscale.  Half the bytes per traversal step: one 256-bit load, and
+  // the 3.4 M inner nodes of the 5.2 M-triangle scene (107 MB) fit the L2
+  const float4* bvh_q;
+  float bvh_qoff[3], bvh_qscale[3];
+  int bvh_quant;             // 1: traverse bvh_q (default), 0: traverse bvh_wide (IPT_BVH_QUANT=0, developer A/B)
   int bvh_root_desc;         // descriptor of the root (0 = inner node 0, negative = the root is a leaf)
   int bvh_depth;             // levels of the tree = entries of the per-thread traversal stack (<= 64)
   const int* bvh_prims;      // triangle index per BVH slot

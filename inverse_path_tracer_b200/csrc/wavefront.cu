@@ -338,6 +338,24 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_accumulate(const float* __restr
   }
 }
 
+// gradient contribution of one vertex: the lanes of a warp that reached this point with the same triangle -- in a BVH scene
+// most vertices lie on the few room triangles around the mesh -- add up by shuffles and the lowest of them issues the three
+// atomics.  Per lane, the same-address double atomics serialise in the L2: the config-5 adjoint took 134 ms, 100 ms of it here.
+__device__ __forceinline__ void wf_grad_add(double* __restrict__ grad, int tri, float g0, float g1, float g2) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned peers = __match_any_sync(__activemask(), tri);
+  const int leader = __ffs(peers) - 1;
+  for (unsigned rest = peers & (peers - 1u); rest; rest &= rest - 1u) {
+    const int src = __ffs(rest) - 1;
+    const float b0 = __shfl_sync(peers, g0, src), b1 = __shfl_sync(peers, g1, src), b2 = __shfl_sync(peers, g2, src);
+    if ((int)lane == leader) { g0 += b0; g1 += b1; g2 += b2; }
+  }
+  if ((int)lane == leader) {
+    double* gg = grad + 3 * (size_t)tri;
+    atomicAdd(gg + 0, (double)g0); atomicAdd(gg + 1, (double)g1); atomicAdd(gg + 2, (double)g2);
+  }
+}
+
 // backward sweep of the adjoint over the recorded vertices of a batch (the deferred sweep of k_paths<GRAD>, one thread
 // per path; for a fixed bounce the threads of a warp read consecutive vertices):
 //   Pbar_k = (E + D_k) + T_k Pbar_{k+1},   dL/dKd[t_k] += P_k (Ke_l g_k + b_k Pbar_{k+1}),   miss: the stale D_{k-1} is re-added with P_k
@@ -368,9 +386,8 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_sweep(DevScene sc, WfBatch b, W
         const float vb = va.y, vg = va.w;
         float k0 = 0.0f, k1 = 0.0f, k2 = 0.0f;
         if (vlight >= 0) { const float4 lke = __ldg(&mat[1 * nT + vlight]); k0 = lke.x * vg; k1 = lke.y * vg; k2 = lke.z * vg; }
-        const float g0 = vP.x * fmaf(vb, pb0, k0), g1 = vP.y * fmaf(vb, pb1, k1), g2 = vP.z * fmaf(vb, pb2, k2);
-        double* gg = grad + 3 * (size_t)vtri;
-        atomicAdd(gg + 0, (double)(w0 * g0)); atomicAdd(gg + 1, (double)(w1 * g1)); atomicAdd(gg + 2, (double)(w2 * g2));
+        float g0 = w0 * (vP.x * fmaf(vb, pb0, k0)), g1 = w1 * (vP.y * fmaf(vb, pb1, k1)), g2 = w2 * (vP.z * fmaf(vb, pb2, k2));
+        wf_grad_add(grad, vtri, g0, g1, g2);
         if (rec.vf4 == 2) {
           pb0 = fmaf(kd.x * vb, pb0, se0 + kd.x * k0); pb1 = fmaf(kd.y * vb, pb1, se1 + kd.y * k1); pb2 = fmaf(kd.z * vb, pb2, se2 + kd.z * k2);
         } else {
@@ -387,8 +404,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_sweep(DevScene sc, WfBatch b, W
             const float4 lke = __ldg(&mat[1 * nT + ulight]);
             const float ug = ua.w;
             const float k0 = lke.x * ug, k1 = lke.y * ug, k2 = lke.z * ug;
-            double* gg = grad + 3 * (size_t)utri;
-            atomicAdd(gg + 0, (double)(w0 * (vP.x * k0))); atomicAdd(gg + 1, (double)(w1 * (vP.y * k1))); atomicAdd(gg + 2, (double)(w2 * (vP.z * k2)));
+            wf_grad_add(grad, utri, w0 * (vP.x * k0), w1 * (vP.y * k1), w2 * (vP.z * k2));
             float f0, f1, f2;
             if (rec.vf4 == 2) { const float4 kd = __ldg(&mat[utri]); f0 = kd.x; f1 = kd.y; f2 = kd.z; }
             else { const float4 ud = up[3]; f0 = ud.x; f1 = ud.y; f2 = ud.z; }
