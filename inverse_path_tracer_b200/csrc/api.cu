@@ -345,10 +345,6 @@ static int upload_scene(SceneHandle* h) {
         quant[2 * i + 1] = make_float4(ubits(w[4]), ubits(w[5]), wide[4 * i + 0].w, wide[4 * i + 1].w);   // + descriptors of the left / right child
       }
     }
-    {
-      const char* qenv = getenv("IPT_BVH_QUANT");   // developer A/B: 0 = float records
-      h->bvh_quant = (qenv && *qenv) ? (atoi(qenv) != 0) : 1;
-    }
     IPT_CUDA(cudaMalloc(&h->bvh_q, std::max<size_t>(quant.size(), 2) * sizeof(float4)));
     if (!quant.empty()) IPT_CUDA(cudaMemcpy(h->bvh_q, quant.data(), quant.size() * sizeof(float4), cudaMemcpyHostToDevice));
     h->bvh_root_desc = nodes.empty() ? 0 : desc_of(0);

@@ -45,7 +45,6 @@ struct DevScene {
   // the 3.4 M inner nodes of the 5.2 M-triangle scene (107 MB) fit the L2
   const float4* bvh_q;
   float bvh_qoff[3], bvh_qscale[3];
-  int bvh_quant;             // 1: traverse bvh_q (default), 0: traverse bvh_wide (IPT_BVH_QUANT=0, developer A/B)
   int bvh_root_desc;         // descriptor of the root (0 = inner node 0, negative = the root is a leaf)
   int bvh_depth;             // levels of the tree = entries of the per-thread traversal stack (<= 64)
   const int* bvh_prims;      // triangle index per BVH slot

@@ -54,7 +54,6 @@ struct SceneHandle {
   float4* bvh_wide = nullptr;
   float4* bvh_q = nullptr;
   float bvh_qoff[3] = {0, 0, 0}, bvh_qscale[3] = {1, 1, 1};
-  int bvh_quant = 1;
   int bvh_root_desc = 0;
   int bvh_depth = 1;
   int* bvh_prims = nullptr;
@@ -88,7 +87,7 @@ struct SceneHandle {
 
   DevScene dev() const {
     DevScene d;
-    d.geom = geom; d.stream = bf_stream; d.nGroups = n_groups; d.nStream = n_stream; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_q = bvh_q; d.bvh_quant = bvh_quant; for (int k = 0; k < 3; k++) { d.bvh_qoff[k] = bvh_qoff[k]; d.bvh_qscale[k] = bvh_qscale[k]; } d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
+    d.geom = geom; d.stream = bf_stream; d.nGroups = n_groups; d.nStream = n_stream; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_q = bvh_q; for (int k = 0; k < 3; k++) { d.bvh_qoff[k] = bvh_qoff[k]; d.bvh_qscale[k] = bvh_qscale[k]; } d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
     d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.nBig = n_big; d.use_bvh = use_bvh ? 1 : 0; d.plain = (!host.any_vn && !host.any_specular) ? 1 : 0;
     memcpy(d.cam, host.cam, sizeof(d.cam));
     return d;
