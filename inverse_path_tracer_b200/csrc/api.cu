@@ -312,8 +312,11 @@ static int upload_scene(SceneHandle* h) {
     // quantised traversal records (device_scene.h): 16 bits per coordinate on the padded root box, lower bounds rounded
     // down and upper bounds up (checked against the float the kernel reconstructs), so a quantised box contains its
     // float box: the closest hit is a minimum over all triangles that pass their own test, a larger box never changes it
-    std::vector<float4> quant(2 * nodes.size(), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
-    if (!nodes.empty()) {
+    std::vector<float4> quant;
+#if IPT_BVH_QUANT
+    quant.assign(2 * nodes.size(), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+#endif
+    if (!quant.empty()) {
       for (int k = 0; k < 3; k++) {
         const float lo = (&packed[0].x)[k], hi = (&packed[1].x)[k];
         h->bvh_qoff[k] = lo;

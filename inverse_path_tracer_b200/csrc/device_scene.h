@@ -23,6 +23,14 @@
 #include "ipt_math.cuh"
 #include <stdint.h>
 
+// BVH traversal records: 0 (default) = 64-byte float records (bvh_wide); 1 = 32-byte records with 16-bit quantised child
+// boxes (bvh_q).  Built and measured in round 2 (profiles/r02_config5.txt): half the bytes per step and the 3.4 M inner
+// nodes of the 5.2 M-triangle scene inside the L2, yet neither the frame (31.2 vs 30.9 ms) nor the incoherent rate
+// (5.2 vs 5.2 Grays/s) moved -- the traversal is not bound by node bytes -- so the simpler float records stay.
+#ifndef IPT_BVH_QUANT
+#define IPT_BVH_QUANT 0
+#endif
+
 namespace ipt {
 
 enum : int { TRI_HAS_VN = 1, TRI_SPECULAR = 2, TRI_ANY_KS = 4, TRI_NEG_Z = 8 /* normal.z == -1: R = -I, path_trace.cu:99-100 */ };
@@ -39,7 +47,7 @@ struct DevScene {
   const float4* vtx;
   const float4* bvh_nodes;   // null in brute-force mode; canonical 32-byte nodes (root box, layout parity)
   const float4* bvh_wide;    // 64-byte traversal records: both child boxes + child descriptors per inner node (IPT_BVH_QUANT == 0 builds)
-  // 32-byte traversal records (default): both child boxes quantised to 16 bits per coordinate on the tree's root box,
+  // 32-byte traversal records (IPT_BVH_QUANT == 1 builds): both child boxes quantised to 16 bits per coordinate on the tree's root box,
   // rounded outwards -- six words {lo_l.x|lo_l.y<<16, lo_l.z|hi_l.x<<16, hi_l.y|hi_l.z<<16, same for the right child} + the two
   // child descriptors.  coordinate = bvh_qoff + q * bvh_qscale.  Half the bytes per traversal step: one 256-bit load, and
   // the 3.4 M inner nodes of the 5.2 M-triangle scene (107 MB) fit the L2

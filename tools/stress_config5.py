@@ -102,7 +102,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--sort-rays", type=int, default=0, help="sort the incoherent test rays by an n-bit Morton cell + octant first")
     ap.add_argument("--cache-dir", default="", help="keep the generated OBJ files here and reuse them")
-    ap.add_argument("--only-render", type=int, default=0, help="1/2: render with that integrator only and exit (profiling)")
+    ap.add_argument("--only-render", type=int, default=0, help="1/2: render with that integrator only and exit (profiling); 4: adjoint pass only")
     a = ap.parse_args()
     t0 = time.time()
     objects, n_tris = stress_scene_objects(a.levels, a.cache_dir)
@@ -116,6 +116,14 @@ def main():
         t_load, sc.nT, sc.nE, sc.n_nodes, sc.uses_bvh, sc.n_large, L.iptKernelLaunchCount() - k0))
     if a.only_render == 3:
         pass
+    elif a.only_render == 4:   # adjoint replay (wavefront: recorded vertices + backward sweep), for launch lists
+        tgt = np.random.RandomState(1).randint(0, 256, (a.size, a.size, 3)).astype(np.uint8)
+        for rep in range(a.reps):
+            p = ipt.default_params(width=a.size, height=a.size, spp=a.spp, max_depth=a.depth, seed=rep)
+            loss, grad, img = sc.render_grad(p, tgt)
+            km = sc.kernel_times_ms(2)
+            print("render_grad: loss %.6f |grad|max %.3e  adjoint %.1f ms, forward %.1f ms" % (loss, float(np.abs(grad).max()), km[0], km[1]))
+        return
     elif a.only_render:
         sc.set_integrator(a.only_render, 0)
         for rep in range(a.reps):
