@@ -226,6 +226,16 @@ static int upload_scene(SceneHandle* h) {
   }
   if (h->use_bvh && rest.empty() && brute.empty()) for (size_t i = 0; i < nT; i++) rest.push_back((int)i);
   h->n_big = h->use_bvh ? (int)brute.size() : 0;
+  if (h->n_big > 0) {
+    // triangle -> index in the brute-force set (255 = in the tree): the wavefront adjoint privatises the gradient of these
+    // few, heavily hit triangles per warp in shared memory (k_wf_sweep)
+    std::vector<unsigned char> slot(nT, 255);
+    for (size_t i = 0; i < brute.size(); i++) slot[brute[i]] = (unsigned char)i;
+    IPT_CUDA(cudaMalloc(&h->big_slot, nT));
+    IPT_CUDA(cudaMemcpy(h->big_slot, slot.data(), nT, cudaMemcpyHostToDevice));
+    IPT_CUDA(cudaMalloc(&h->big_tri, brute.size() * sizeof(int)));
+    IPT_CUDA(cudaMemcpy(h->big_tri, brute.data(), brute.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
   if (!brute.empty()) {
     std::vector<float4> planes, edges;
     std::vector<int2> grange, slot_tri;

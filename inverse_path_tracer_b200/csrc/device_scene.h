@@ -57,6 +57,8 @@ struct DevScene {
   int bvh_depth;             // levels of the tree = entries of the per-thread traversal stack (<= 64)
   const int* bvh_prims;      // triangle index per BVH slot
   int nT, nE, nNodes;
+  const unsigned char* big_slot;   // BVH scenes: per triangle, its index in the brute-force set (255: in the tree); null without a set
+  const int* big_tri;              // ... and the triangle id of every member of the set [nBig]
   int nBig;                  // BVH scenes: triangles kept out of the tree and tested brute force (`stream` describes them)
   int use_bvh;
   int plain;                 // no per-vertex normals and no specular lobe anywhere in the scene

@@ -59,6 +59,8 @@ struct SceneHandle {
   int* bvh_prims = nullptr;
   int n_nodes = 0;
   int n_big = 0;
+  unsigned char* big_slot = nullptr;
+  int* big_tri = nullptr;
   bool use_bvh = false;
   bool host_only = false;
   bool kd_dirty = false;      // the device albedos were changed on the device (iptSetMaterialsDevice, iptInverseStep): getMaterials reads them back
@@ -88,7 +90,7 @@ struct SceneHandle {
   DevScene dev() const {
     DevScene d;
     d.geom = geom; d.stream = bf_stream; d.nGroups = n_groups; d.nStream = n_stream; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_q = bvh_q; for (int k = 0; k < 3; k++) { d.bvh_qoff[k] = bvh_qoff[k]; d.bvh_qscale[k] = bvh_qscale[k]; } d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
-    d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.nBig = n_big; d.use_bvh = use_bvh ? 1 : 0; d.plain = (!host.any_vn && !host.any_specular) ? 1 : 0;
+    d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.nBig = n_big; d.big_slot = big_slot; d.big_tri = big_tri; d.use_bvh = use_bvh ? 1 : 0; d.plain = (!host.any_vn && !host.any_specular) ? 1 : 0;
     memcpy(d.cam, host.cam, sizeof(d.cam));
     return d;
   }
@@ -96,7 +98,7 @@ struct SceneHandle {
     if (host_only) return;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
-    cudaFree(geom); cudaFree(bf_stream); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_wide); cudaFree(bvh_q); cudaFree(bvh_prims);
+    cudaFree(geom); cudaFree(bf_stream); cudaFree(mat); cudaFree(light); cudaFree(vtx); cudaFree(bvh_nodes); cudaFree(bvh_wide); cudaFree(bvh_q); cudaFree(big_slot); cudaFree(big_tri); cudaFree(bvh_prims);
     Scratch* all[] = {&wavefront, &partial, &counters, &cnt_out, &trace_counter, &block_acc, &vstacks, &acc, &dldpx, &img, &img8, &target, &raw, &lossgrad, &rays, &hits_tri, &hits_t};
     for (Scratch* s : all) s->release();
     if (host_live) cudaFreeHost(host_live);

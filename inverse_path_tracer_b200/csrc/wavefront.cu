@@ -338,22 +338,31 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_accumulate(const float* __restr
   }
 }
 
-// gradient contribution of one vertex: the lanes of a warp that reached this point with the same triangle -- in a BVH scene
-// most vertices lie on the few room triangles around the mesh -- add up by shuffles and the lowest of them issues the three
-// atomics.  Per lane, the same-address double atomics serialise in the L2: the config-5 adjoint took 134 ms, 100 ms of it here.
-__device__ __forceinline__ void wf_grad_add(double* __restrict__ grad, int tri, float g0, float g1, float g2) {
+// gradient contribution of one vertex.  In a room-plus-mesh scene most vertices lie on the few room triangles -- the scene's
+// brute-force set -- and per-lane double atomics on those ~50 addresses serialise in the L2 (the config-5 adjoint took 134 ms, 100 of
+// them here; 78 ms with warp aggregation in front of the global atomics).  So: lanes that hit the same triangle of the set add up by
+// shuffles, the lowest of them adds the sum to the WARP's private accumulator in shared memory (one address per triangle and
+// channel, written by one lane per step: no atomics), and the block flushes once at the end.  Mesh triangles (millions of
+// addresses, no contention) go straight to the global array.
+constexpr int kSweepBigMax = 128;   // kBruteForceMaxTris
+__device__ __forceinline__ void wf_grad_add(double* __restrict__ grad, const unsigned char* __restrict__ big_slot, float* __restrict__ wacc, int tri,
+                                            float g0, float g1, float g2) {
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned peers = __match_any_sync(__activemask(), tri);
+  const int slot = big_slot ? (int)__ldg(&big_slot[tri]) : 255;
+  if (slot == 255) {
+    double* gg = grad + 3 * (size_t)tri;
+    atomicAdd(gg + 0, (double)g0); atomicAdd(gg + 1, (double)g1); atomicAdd(gg + 2, (double)g2);
+    return;
+  }
+  const unsigned peers = __match_any_sync(__activemask(), slot);
   const int leader = __ffs(peers) - 1;
   for (unsigned rest = peers & (peers - 1u); rest; rest &= rest - 1u) {
     const int src = __ffs(rest) - 1;
     const float b0 = __shfl_sync(peers, g0, src), b1 = __shfl_sync(peers, g1, src), b2 = __shfl_sync(peers, g2, src);
     if ((int)lane == leader) { g0 += b0; g1 += b1; g2 += b2; }
   }
-  if ((int)lane == leader) {
-    double* gg = grad + 3 * (size_t)tri;
-    atomicAdd(gg + 0, (double)g0); atomicAdd(gg + 1, (double)g1); atomicAdd(gg + 2, (double)g2);
-  }
+  if ((int)lane == leader) { wacc[3 * slot] += g0; wacc[3 * slot + 1] += g1; wacc[3 * slot + 2] += g2; }
+  __syncwarp(peers);
 }
 
 // backward sweep of the adjoint over the recorded vertices of a batch (the deferred sweep of k_paths<GRAD>, one thread
@@ -362,6 +371,11 @@ __device__ __forceinline__ void wf_grad_add(double* __restrict__ grad, int tri, 
 // Gradient contributions are weighted by dLoss/dL of the path's pixel (dldpx, shard-local pixel index) and added to
 // grad[3 nT] with double atomics (BVH scenes have too many triangles for per-block tiles).
 __global__ void __launch_bounds__(kWfBlock) k_wf_sweep(DevScene sc, WfBatch b, WfRecord rec, const float* __restrict__ dldpx, double* __restrict__ grad) {
+  __shared__ float s_acc[(kWfBlock / 32) * 3 * kSweepBigMax];   // one private accumulator per warp for the brute-force set
+  for (int i = threadIdx.x; i < (kWfBlock / 32) * 3 * kSweepBigMax; i += blockDim.x) s_acc[i] = 0.0f;
+  __syncthreads();
+  float* wacc = s_acc + (threadIdx.x >> 5) * 3 * kSweepBigMax;
+  const unsigned char* __restrict__ big_slot = sc.big_slot;
   const int n = b.tile_n * b.ns;
   const size_t cap = (size_t)b.cap;
   const int nT = sc.nT;
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_sweep(DevScene sc, WfBatch b, W
         float k0 = 0.0f, k1 = 0.0f, k2 = 0.0f;
         if (vlight >= 0) { const float4 lke = __ldg(&mat[1 * nT + vlight]); k0 = lke.x * vg; k1 = lke.y * vg; k2 = lke.z * vg; }
         float g0 = w0 * (vP.x * fmaf(vb, pb0, k0)), g1 = w1 * (vP.y * fmaf(vb, pb1, k1)), g2 = w2 * (vP.z * fmaf(vb, pb2, k2));
-        wf_grad_add(grad, vtri, g0, g1, g2);
+        wf_grad_add(grad, big_slot, wacc, vtri, g0, g1, g2);
         if (rec.vf4 == 2) {
           pb0 = fmaf(kd.x * vb, pb0, se0 + kd.x * k0); pb1 = fmaf(kd.y * vb, pb1, se1 + kd.y * k1); pb2 = fmaf(kd.z * vb, pb2, se2 + kd.z * k2);
         } else {
@@ -404,7 +418,7 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_sweep(DevScene sc, WfBatch b, W
             const float4 lke = __ldg(&mat[1 * nT + ulight]);
             const float ug = ua.w;
             const float k0 = lke.x * ug, k1 = lke.y * ug, k2 = lke.z * ug;
-            wf_grad_add(grad, utri, w0 * (vP.x * k0), w1 * (vP.y * k1), w2 * (vP.z * k2));
+            wf_grad_add(grad, big_slot, wacc, utri, w0 * (vP.x * k0), w1 * (vP.y * k1), w2 * (vP.z * k2));
             float f0, f1, f2;
             if (rec.vf4 == 2) { const float4 kd = __ldg(&mat[utri]); f0 = kd.x; f1 = kd.y; f2 = kd.z; }
             else { const float4 ud = up[3]; f0 = ud.x; f1 = ud.y; f2 = ud.z; }
@@ -414,6 +428,14 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_sweep(DevScene sc, WfBatch b, W
         pb0 = c0; pb1 = c1; pb2 = c2;
       }
     }
+  }
+  // flush the warps' private sums of the brute-force set: one double atomic per triangle and channel per block
+  __syncthreads();
+  const int nb = min(sc.nBig, kSweepBigMax);
+  for (int i = threadIdx.x; i < 3 * nb; i += blockDim.x) {
+    float a = 0.0f;
+    for (int w = 0; w < kWfBlock / 32; w++) a += s_acc[w * 3 * kSweepBigMax + i];
+    if (a != 0.0f) atomicAdd(grad + 3 * (size_t)sc.big_tri[i / 3] + (i % 3), (double)a);
   }
 }
 
