@@ -329,34 +329,88 @@ static int upload_scene(SceneHandle* h) {
     if (!quant.empty()) {
       for (int k = 0; k < 3; k++) {
         const float lo = (&packed[0].x)[k], hi = (&packed[1].x)[k];
-        h->bvh_qoff[k] = lo;
-        h->bvh_qscale[k] = (hi > lo) ? (hi - lo) / 65535.0f * 1.0000005f : 1.0f;
+        // two grid steps of margin on either side: every box is padded outwards by one more step than rounding needs
+        // (the kernel's folded decode is exact to half a step, intersect.cuh)
+        h->bvh_qscale[k] = (hi > lo) ? (hi - lo) / 65531.0f * 1.0000005f : 1.0f;
+        h->bvh_qoff[k] = lo - 2.0f * h->bvh_qscale[k];
       }
       auto qlo = [&](float v, int k) {
         int q = (int)floorf((v - h->bvh_qoff[k]) / h->bvh_qscale[k]);
         q = std::max(0, std::min(65535, q));
         while (q > 0 && fmaf((float)q, h->bvh_qscale[k], h->bvh_qoff[k]) > v) q--;
-        return (unsigned)q;
+        return (unsigned)std::max(0, q - 1);
       };
       auto qhi = [&](float v, int k) {
         int q = (int)ceilf((v - h->bvh_qoff[k]) / h->bvh_qscale[k]);
         q = std::max(0, std::min(65535, q));
         while (q < 65535 && fmaf((float)q, h->bvh_qscale[k], h->bvh_qoff[k]) < v) q++;
-        return (unsigned)q;
+        return (unsigned)std::min(65535, q + 1);
       };
       auto ubits = [](unsigned v) { float f; memcpy(&f, &v, 4); return f; };
+      auto qbox = [&](size_t c, unsigned* w) {   // three words of the quantised (padded) box of binary node c
+        const float4 blo = packed[2 * c], bhi = packed[2 * c + 1];
+        const unsigned lx = qlo(blo.x, 0), ly = qlo(blo.y, 1), lz = qlo(blo.z, 2), hx = qhi(bhi.x, 0), hy = qhi(bhi.y, 1), hz = qhi(bhi.z, 2);
+        w[0] = lx | (ly << 16); w[1] = lz | (hx << 16); w[2] = hy | (hz << 16);
+      };
+#if IPT_BVH_QUANT == 2
+      // 4-wide collapse of the binary tree: the 4-node headed by binary inner node i holds the children of i's children (a
+      // child of i that is a leaf stays as it is), i.e. every other level of the binary tree disappears.  Records (64 bytes,
+      // one 128-byte line holds two): 4 x 3 words of quantised boxes, 4 descriptors (>= 0: 4-node index, < 0: leaf as
+      // before; an empty slot is a point box at the grid corner with the descriptor of a leaf without triangles).  4-nodes
+      // are numbered in depth-first order.  `held` = stack entries a ray can hold when it arrives at the node (every
+      // ancestor may have pushed all its other children): the bound on the traversal stack.
+      struct Node4 { size_t ch[4]; int nc; };
+      std::vector<int> id4(nodes.size(), -1);
+      std::vector<Node4> n4;
+      int stack_need = 1;
+      if (nodes[0].rightOffset != 0) {
+        std::vector<std::pair<size_t, int>> todo;
+        todo.emplace_back((size_t)0, 0);
+        while (!todo.empty()) {
+          const size_t i = todo.back().first;
+          const int held = todo.back().second;
+          todo.pop_back();
+          id4[i] = (int)n4.size();
+          Node4 nd;
+          nd.nc = 0;
+          const size_t lr[2] = {i + 1, i + (size_t)nodes[i].rightOffset};
+          for (size_t c : lr) {
+            if (nodes[c].rightOffset != 0) { nd.ch[nd.nc++] = c + 1; nd.ch[nd.nc++] = c + (size_t)nodes[c].rightOffset; }
+            else nd.ch[nd.nc++] = c;
+          }
+          stack_need = std::max(stack_need, held + nd.nc - 1);
+          for (int k = nd.nc - 1; k >= 0; k--)
+            if (nodes[nd.ch[k]].rightOffset != 0) todo.emplace_back(nd.ch[k], held + nd.nc - 1);
+          n4.push_back(nd);
+        }
+      }
+      quant.assign(4 * std::max<size_t>(n4.size(), 1), make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+      for (size_t n = 0; n < n4.size(); n++) {
+        unsigned w[16];
+        for (int k = 0; k < 4; k++) {
+          if (k < n4[n].nc) {
+            const size_t c = n4[n].ch[k];
+            qbox(c, w + 3 * k);
+            w[12 + k] = (unsigned)(nodes[c].rightOffset != 0 ? id4[c] : desc_of(c));
+          } else {
+            w[3 * k] = 0xffffffffu; w[3 * k + 1] = 0xffffffffu; w[3 * k + 2] = 0xffffffffu;
+            w[12 + k] = 0xffffffffu;   // ~0: leaf, start 0, no triangles
+          }
+        }
+        for (int q = 0; q < 4; q++) quant[4 * n + q] = make_float4(ubits(w[4 * q]), ubits(w[4 * q + 1]), ubits(w[4 * q + 2]), ubits(w[4 * q + 3]));
+      }
+      max_depth = stack_need + 1;
+      if (max_depth > 64) return fail("BVH too deep for the 64-entry traversal stack");
+#else
       for (size_t i = 0; i < nodes.size(); i++) {
         if (nodes[i].rightOffset == 0) continue;
         const size_t ch[2] = {i + 1, i + (size_t)nodes[i].rightOffset};
         unsigned w[6];
-        for (int c = 0; c < 2; c++) {
-          const float4 blo = packed[2 * ch[c]], bhi = packed[2 * ch[c] + 1];
-          const unsigned lx = qlo(blo.x, 0), ly = qlo(blo.y, 1), lz = qlo(blo.z, 2), hx = qhi(bhi.x, 0), hy = qhi(bhi.y, 1), hz = qhi(bhi.z, 2);
-          w[3 * c + 0] = lx | (ly << 16); w[3 * c + 1] = lz | (hx << 16); w[3 * c + 2] = hy | (hz << 16);
-        }
+        for (int c = 0; c < 2; c++) qbox(ch[c], w + 3 * c);
         quant[2 * i] = make_float4(ubits(w[0]), ubits(w[1]), ubits(w[2]), ubits(w[3]));
         quant[2 * i + 1] = make_float4(ubits(w[4]), ubits(w[5]), wide[4 * i + 0].w, wide[4 * i + 1].w);   // + descriptors of the left / right child
       }
+#endif
     }
     IPT_CUDA(cudaMalloc(&h->bvh_q, std::max<size_t>(quant.size(), 2) * sizeof(float4)));
     if (!quant.empty()) IPT_CUDA(cudaMemcpy(h->bvh_q, quant.data(), quant.size() * sizeof(float4), cudaMemcpyHostToDevice));
@@ -371,10 +425,17 @@ static int upload_scene(SceneHandle* h) {
       IPT_CUDA(cudaMemcpy(h->bvh_nodes, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice));
       IPT_CUDA(cudaMemcpy(h->bvh_prims, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
       // leaf triangles are read in tree order: store their records that way (slot j = triangle perm[j]), so a leaf is
-      // one contiguous run and the id lookup is only needed for accepted hits
-      std::vector<float4> leaf_geom(4 * perm.size());
-      for (size_t j = 0; j < perm.size(); j++) memcpy(&leaf_geom[4 * j], &geom[4 * (size_t)perm[j]], 4 * sizeof(float4));
+      // one contiguous run and the id lookup is only needed for accepted hits.  Planes first ([n] float4), then the edge
+      // planes ([3 n]): a leaf visit reads the planes of all its triangles at once and the 48 bytes of edges only for the
+      // triangles whose plane test passes
+      const size_t n_slots = perm.size();
+      std::vector<float4> leaf_geom(4 * n_slots);
+      for (size_t j = 0; j < n_slots; j++) {
+        leaf_geom[j] = geom[4 * (size_t)perm[j]];
+        memcpy(&leaf_geom[n_slots + 3 * j], &geom[4 * (size_t)perm[j] + 1], 3 * sizeof(float4));
+      }
       IPT_CUDA(cudaMemcpy(h->geom, leaf_geom.data(), leaf_geom.size() * sizeof(float4), cudaMemcpyHostToDevice));
+      h->geom_edges = h->geom + n_slots;
     }
   }
   return 0;

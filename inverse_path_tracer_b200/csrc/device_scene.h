@@ -2,7 +2,7 @@
 //
 // HBM layout.  All arrays are float4-vectorised so one triangle test is
 // four 16-byte loads and the whole small scene can be staged into shared memory with float4 copies.
-//   geom  [4*nT] : {n.xyz, k=dot(c,n)} {e0.xyz,e0.d} {e1.xyz,e1.d} {e2.xyz,e2.d}     64 B / triangle (BVH leaves)
+//   geom  [nT] : {n.xyz, k=dot(c,n)}, geom_edges [3*nT] : {e0.xyz,e0.d} {e1.xyz,e1.d} {e2.xyz,e2.d}     16 + 48 B / triangle, leaf order (BVH leaves)
 //   stream [nStream] : the brute-force set as ONE record stream, walked with a single running address:
 //     per plane group (triangles whose (n, k) are value-equal share one plane test)
 //       {n.xyz, k}                                 the plane
@@ -16,19 +16,24 @@
 //   vtx   [5*nT] : {v0.xyz, vn0.x} {v1.xyz, vn0.y} {v2.xyz, vn0.z} {vn1.xyz, area} {vn2.xyz, 0}
 //                  (only read for triangles that carry per-vertex normals: Triangle::getNormal)
 //   bvh nodes [2*nNodes] : {lo.xyz, rightOffset(bits)} {hi.xyz, start<<3|nPrims (bits)}   32 B / node (canonical DFS layout)
-//   bvh wide  [4*nNodes] : {L.lo, desc L} {L.hi, desc R} {R.lo, -} {R.hi, -}             64 B / inner node (traversal)
+//   bvh wide  [4*nNodes] : {L.lo, desc L} {L.hi, desc R} {R.lo, -} {R.hi, -}             64 B / inner node (float traversal records)
+//   bvh q     [2*nNodes] : 6 words of 16-bit child box coordinates + 2 child descriptors   32 B / inner node (default traversal records)
 #pragma once
 #include <cuda_runtime.h>
 
 #include "ipt_math.cuh"
 #include <stdint.h>
 
-// BVH traversal records: 0 (default) = 64-byte float records (bvh_wide); 1 = 32-byte records with 16-bit quantised child
-// boxes (bvh_q).  Built and measured in round 2 (profiles/r02_config5.txt): half the bytes per step and the 3.4 M inner
-// nodes of the 5.2 M-triangle scene inside the L2, yet neither the frame (31.2 vs 30.9 ms) nor the incoherent rate
-// (5.2 vs 5.2 Grays/s) moved -- the traversal is not bound by node bytes -- so the simpler float records stay.
+// BVH traversal records (all three built and measured in round 2, profiles/r02_config5.txt; results are identical by construction --
+// a quantised box contains its float box):
+//   0 = 64-byte float records of a binary node (bvh_wide)                                   29.8 ms frame, 5.0 Grays/s incoherent
+//   1 = 32-byte records, both child boxes at 16 bits per coordinate on the root box (bvh_q)  29.0 - 29.4 ms, 5.3 Grays/s   <- default
+//   2 = 4-wide collapse of the tree, four 16-bit child boxes in 64 bytes (bvh_q)             33.5 ms, 4.8 Grays/s
+// Half the bytes per step (1) or half the dependent fetches per ray (2) move the kernel by a few per cent either way: what it
+// runs out of is issue slots at 16 of 32 lanes, not bytes or latency.  (1) also halves the node memory (215 -> 107 MB for 5.2 M
+// triangles: inside the L2).
 #ifndef IPT_BVH_QUANT
-#define IPT_BVH_QUANT 0
+#define IPT_BVH_QUANT 1
 #endif
 
 namespace ipt {
@@ -38,7 +43,8 @@ enum : int { TRI_HAS_VN = 1, TRI_SPECULAR = 2, TRI_ANY_KS = 4, TRI_NEG_Z = 8 /* 
 constexpr int kMatStride = 8;   // float4 records per triangle in `mat`
 
 struct DevScene {
-  const float4* geom;          // [4 nT] plane + 3 edge planes per triangle; in BVH scenes stored in leaf order (slot j = triangle bvh_prims[j])
+  const float4* geom;          // BVH scenes: plane {n, k} of leaf slot j (slot j = triangle bvh_prims[j]), [n slots] ...
+  const float4* geom_edges;    // ... and its three edge planes [3 n slots]
   const float4* stream;     // record stream of the brute-force set (see above)
   int nGroups;
   int nStream;              // float4 records in `stream`

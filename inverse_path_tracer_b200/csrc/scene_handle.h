@@ -44,6 +44,7 @@ struct SceneHandle {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   float4* geom = nullptr;
+  float4* geom_edges = nullptr;   // BVH scenes: edge planes of the leaf slots (inside the geom allocation)
   float4* bf_stream = nullptr;   // record stream of the brute-force set (device_scene.h)
   int n_groups = 0;
   int n_stream = 0;
@@ -89,7 +90,7 @@ struct SceneHandle {
 
   DevScene dev() const {
     DevScene d;
-    d.geom = geom; d.stream = bf_stream; d.nGroups = n_groups; d.nStream = n_stream; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_q = bvh_q; for (int k = 0; k < 3; k++) { d.bvh_qoff[k] = bvh_qoff[k]; d.bvh_qscale[k] = bvh_qscale[k]; } d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
+    d.geom = geom; d.geom_edges = geom_edges; d.stream = bf_stream; d.nGroups = n_groups; d.nStream = n_stream; d.mat = mat; d.light = light; d.vtx = vtx; d.bvh_nodes = bvh_nodes; d.bvh_wide = bvh_wide; d.bvh_q = bvh_q; for (int k = 0; k < 3; k++) { d.bvh_qoff[k] = bvh_qoff[k]; d.bvh_qscale[k] = bvh_qscale[k]; } d.bvh_root_desc = bvh_root_desc; d.bvh_depth = bvh_depth; d.bvh_prims = bvh_prims;
     d.nT = (int)host.tris.size(); d.nE = (int)host.emissives.size(); d.nNodes = n_nodes; d.nBig = n_big; d.big_slot = big_slot; d.big_tri = big_tri; d.use_bvh = use_bvh ? 1 : 0; d.plain = (!host.any_vn && !host.any_specular) ? 1 : 0;
     memcpy(d.cam, host.cam, sizeof(d.cam));
     return d;

@@ -5,6 +5,8 @@
 //   k_trace_rays_bvh   persistent, phased BVH traversal
 //   k_copy16           copy-bandwidth measurement aid (iptMeasureCopyGBps)
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "intersect.cuh"
 #include "kernels.h"
@@ -29,29 +31,32 @@ constexpr int kInnerQuorum = IPT_INNER_QUORUM;
 #define IPT_FETCH_QUORUM 8
 #endif
 constexpr int kFetchQuorum = IPT_FETCH_QUORUM;
+#ifndef IPT_TRACE_MINB
+#define IPT_TRACE_MINB 10   // resident blocks per SM the register allocation aims at (10: 48 registers, no spills; 12: 40 registers, 70 bytes of spills, 2 % slower; 16: 32 registers, 36 % slower)
+#endif
 #ifndef IPT_RAY_CHUNK
 #define IPT_RAY_CHUNK 128
 #endif
 constexpr int kRayChunk = IPT_RAY_CHUNK;
 
 template <bool STATS>
-__global__ void __launch_bounds__(kBlock) k_trace_rays_bvh(DevScene sc, const float* __restrict__ rays, int n_direct, const int* __restrict__ n_live, int cap,
+__global__ void __launch_bounds__(kBlock, IPT_TRACE_MINB) k_trace_rays_bvh(DevScene sc, const float* __restrict__ rays, int n_direct, const int* __restrict__ n_live, int cap,
                                                            int* __restrict__ tri, float* __restrict__ tout, unsigned long long* __restrict__ counter,
                                                            unsigned long long* __restrict__ stats) {
   extern __shared__ float4 smem[];
-  int* col = reinterpret_cast<int*>(smem) + threadIdx.x;
-  const int stride = blockDim.x;
+  const uint32_t col = smem_addr(reinterpret_cast<int*>(smem) + threadIdx.x), stride = blockDim.x * (uint32_t)sizeof(int);
   const unsigned lane = threadIdx.x & 31u;
   // a scene with a brute-force set (large triangles kept out of the tree): k_trace_rays has already written each
   // ray's hit among those into tri / tout; the traversal starts from that bound
   const bool seeded = sc.nGroups > 0;
-  const long long n = n_live ? (long long)*n_live : (long long)n_direct;
-  const long long total = n_live ? 2 * n : n;
+  // a batch has < 2^31 rays (a wavefront bounce: 2 x cap <= 2^25), so ray indices are ints
+  const int n = n_live ? *n_live : n_direct;
+  const int total = n_live ? 2 * n : n;
   unsigned nodes = 0, tris = 0;
   BvhRay r;
   r.cur = kBvhDone;
   r.best_t = INFINITY; r.best_i = -1; r.sp = 0;
-  long long idx = -1;
+  int idx = -1;
   bool exhausted = false;       // the batch has no ray left for this lane
   int chunk_next = 0, chunk_end = 0;   // the warp's current chunk of ray indices (warp-uniform; a batch has < 2^31 rays)
   for (;;) {
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays_bvh(DevScene sc, const fl
       // every warp of the grid hits the same address); a refill takes what is left of the warp's chunk first
       const int need = __popc(wm), rank = __popc(wm & ((1u << lane) - 1u));
       const int left = chunk_end - chunk_next;
-      long long mine;
+      int mine;
       if (need > left) {
         const int leader = __ffs(wm) - 1;
         unsigned long long fresh = 0;
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays_bvh(DevScene sc, const fl
         fresh = __shfl_sync(kFull, fresh, leader);
         // a claim far beyond the batch (the counter keeps growing while warps drain) is clamped: it is exhausted anyway
         const int fb = (int)min(fresh, (unsigned long long)0x7fff0000u);
-        mine = rank < left ? (long long)(chunk_next + rank) : (long long)fb + (rank - left);
+        mine = rank < left ? chunk_next + rank : fb + (rank - left);
         chunk_next = fb + (need - left);
         chunk_end = fb + kRayChunk;
       } else {
@@ -85,14 +90,18 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays_bvh(DevScene sc, const fl
         if (mine >= total) {
           exhausted = true;
         } else {
-          idx = mine < n ? mine : (long long)cap + (mine - n);
-          const float2* r2 = reinterpret_cast<const float2*>(rays + 6 * idx);
+          idx = mine < n ? mine : cap + (mine - n);
+          const float2* r2 = reinterpret_cast<const float2*>(rays + 6 * (size_t)idx);
           const float2 a = __ldg(r2), b = __ldg(r2 + 1), c = __ldg(r2 + 2);
+          // the seed is requested with the ray, not after the "no ray" test: one load latency per fetch instead of two
+          int seed_i = -1;
+          float seed_t = INFINITY;
+          if (seeded) { seed_i = tri[idx]; seed_t = tout[idx]; }
           r.best_i = -1; r.best_t = INFINITY;
           if (!(b.y == 0.0f && c.x == 0.0f && c.y == 0.0f)) {
             const f3 rp = mk3(a.x, a.y, b.x), rd = mk3(b.y, c.x, c.y);
             bvh_begin(sc, r, rp, rd);
-            if (seeded) { r.best_i = tri[idx]; r.best_t = tout[idx]; }
+            r.best_i = seed_i; r.best_t = seed_t;
           }
         }
       }
@@ -115,7 +124,18 @@ __global__ void __launch_bounds__(kBlock) k_trace_rays_bvh(DevScene sc, const fl
       if (inner) bvh_step<STATS>(sc, r, col, stride, &nodes, &tris);
     }
     // ---- leaves ----
-    if (r.cur < 0) bvh_step<STATS>(sc, r, col, stride, &nodes, &tris);
+    if (r.cur < 0) {
+      // the direction is only needed here (the inner phase runs on 1/d): re-read it instead of keeping three registers
+      // alive through the inner loop -- the kernel then fits 32 registers = 16 resident blocks per SM instead of 12
+      const float2* r2 = reinterpret_cast<const float2*>(rays + 6 * (size_t)idx);
+      const float2 b = __ldg(r2 + 1), c = __ldg(r2 + 2);
+      r.d = mk3(b.y, c.x, c.y);
+#if IPT_BVH_QUANT
+      const float2 a = __ldg(r2);   // quantised nodes: the inner phase runs on qa / qb, the origin is leaf-only as well
+      r.p = mk3(a.x, a.y, b.x);
+#endif
+      bvh_step<STATS>(sc, r, col, stride, &nodes, &tris);
+    }
   }
   if (idx >= 0) { tri[idx] = r.best_i; tout[idx] = r.best_t; }
   if (STATS) {
@@ -188,6 +208,12 @@ cudaError_t launch_trace_bounce(const DevScene& sc, const float* rays, const int
   int nb = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_rays_bvh<false>, kBlock, smem);
   if (nb < 1) nb = 1;
+  if (const char* ov = getenv("IPT_TRACE_BLOCKS")) nb = std::max(1, std::min(nb, atoi(ov)));   // occupancy experiments
+  static bool said = false;
+  if (!said && getenv("IPT_TRACE_DEBUG")) {
+    said = true;
+    fprintf(stderr, "ipt: k_trace_rays_bvh: %d blocks/SM, %zu B of stack per block (tree depth %d)\n", nb, smem, sc.bvh_depth);
+  }
   k_trace_rays_bvh<false><<<sm_count * nb, kBlock, smem, st>>>(sc, rays, 0, n_live, cap, tri, t, counter, nullptr);
   *n_launches += 1;
   return cudaGetLastError();

@@ -30,7 +30,10 @@ enum { WF_END_AFTER = 1, WF_SH_VALID = 2, WF_EXT_VALID = 4 };
 #define IPT_WF_BLOCK 256
 #endif
 #ifndef IPT_WF_MINB
-#define IPT_WF_MINB 4
+#define IPT_WF_MINB 3         // k_wf_shade, scenes with a Phong lobe / vertex normals: 80 registers (4 blocks = 64 registers spill 300 bytes per thread)
+#endif
+#ifndef IPT_WF_MINB_PLAIN
+#define IPT_WF_MINB_PLAIN 3   // plain scenes: 80 registers, no spills
 #endif
 constexpr int kWfBlock = IPT_WF_BLOCK;
 
@@ -107,15 +110,14 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(DevScene sc, DevRender
 // one bounce of shading for every live path: second half of directLighting of the previous bounce
 // ([D] of k_paths), then radiance() of this bounce's hit ([A] of k_paths); survivors are appended to the
 // next bounce's arrays
-__global__ void __launch_bounds__(kWfBlock, IPT_WF_MINB) k_wf_shade(DevScene sc, DevRender rp, WfBatch b, int bounce, const float4* __restrict__ sin_, float4* __restrict__ sout,
+template <bool PLAIN, bool RECORD>
+__global__ void __launch_bounds__(kWfBlock, PLAIN ? IPT_WF_MINB_PLAIN : IPT_WF_MINB) k_wf_shade(DevScene sc, DevRender rp, WfBatch b, int bounce, const float4* __restrict__ sin_, float4* __restrict__ sout,
                                                        const float* __restrict__ rin, float* __restrict__ rout, const int* __restrict__ hit_tri,
                                                        const float* __restrict__ hit_t, const int* __restrict__ n_in, int* __restrict__ n_out,
                                                        float* __restrict__ lsamp, unsigned long long* __restrict__ counters, WfRecord rec) {
   const int nT = sc.nT, nE = sc.nE;
   const size_t cap = (size_t)b.cap;
   const int n = *n_in;
-  const bool RECORD = rec.V != nullptr;
-  const bool PLAIN = sc.plain != 0;
   const float4* __restrict__ mat = sc.mat;
   const float4* __restrict__ slight = sc.light;
   const f3 zero3 = mk3(0.0f, 0.0f, 0.0f);
@@ -476,6 +478,8 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
     rec.vlen = (int*)((char*)adj->record + wf_align((size_t)adj->vdepth * c * rec.vf4 * sizeof(float4)));
   }
 
+  // the four variants of the shading kernel: scenes without a Phong lobe / vertex normals (PLAIN), with the adjoint's vertex record
+  auto shade = sc.plain ? (adj ? k_wf_shade<true, true> : k_wf_shade<true, false>) : (adj ? k_wf_shade<false, true> : k_wf_shade<false, false>);
   const int tile_cap = std::min(rp.n_pix, cap);
   const bool unbounded = rp.max_depth <= 0;
   for (int p0 = 0; p0 < rp.n_pix; p0 += tile_cap) {
@@ -503,8 +507,8 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
           if (e != cudaSuccess) return e;
           {
             NvtxRange r("ipt.wavefront.shade");
-            k_wf_shade<<<shade_grid, kWfBlock, 0, st>>>(sc, rp, b, bounce, state[cur], state[cur ^ 1], rays[cur], rays[cur ^ 1], hit_tri, hit_t, n_live + cur,
-                                                       n_live + (cur ^ 1), lsamp, counters, rec);
+            shade<<<shade_grid, kWfBlock, 0, st>>>(sc, rp, b, bounce, state[cur], state[cur ^ 1], rays[cur], rays[cur ^ 1], hit_tri, hit_t, n_live + cur,
+                                                   n_live + (cur ^ 1), lsamp, counters, rec);
           }
           *n_launches += 1;
           cur ^= 1;
