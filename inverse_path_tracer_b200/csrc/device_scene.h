@@ -29,8 +29,8 @@
 //   0 = 64-byte float records of a binary node (bvh_wide)                                   29.8 ms frame, 5.0 Grays/s incoherent
 //   1 = 32-byte records, both child boxes at 16 bits per coordinate on the root box (bvh_q)  29.0 - 29.4 ms, 5.3 Grays/s   <- default
 //   2 = 4-wide collapse of the tree, four 16-bit child boxes in 64 bytes (bvh_q)             33.5 ms, 4.8 Grays/s
-// Half the bytes per step (1) buys 2 %, half the node visits per ray (2) costs 12 %.  Why is not settled: ncu of the binary kernel
-// shows issue slots 54 % busy at 16 of 32 lanes with long-scoreboard stalls on top; the 4-wide build was not profiled.
+// Half the bytes per step (1) buys 2 %, half the node visits per ray (2) costs 12 %: under ncu (2) runs 3 % more instructions and
+// the same number of load requests as (1) (two 256-bit loads per 64-byte node) at a lower issue rate (profiles/r02_trace_bvh_summary.txt).
 // (1) also halves the node memory (215 -> 107 MB for 5.2 M triangles: inside the L2).
 #ifndef IPT_BVH_QUANT
 #define IPT_BVH_QUANT 1
