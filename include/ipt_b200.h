@@ -59,10 +59,11 @@ typedef struct IptRenderParams {
   int group_samples;      /* samples accumulated sequentially per partial sum; a pixel is the sum of its group partials in
                            * group order.  0 (or > spp): spp, i.e. the reference's single running sum (path_trace.cu:190-193).
                            * -1 (the default): chosen from the FULL image size only, so every shard of an image agrees:
-                           * the largest g in {64, 32, ..., 2, 1} with width * height * spp >= g * 2^22 (else 1), i.e. at
+                           * the largest g in {32, 16, ..., 2, 1} with width * height * spp >= g * 2^22 (else 1), i.e. at
                            * least 4 Mi work items.  A group is the unit of work the persistent kernel hands to a lane:
                            * small jobs -- and row shards of them on several GPUs -- need small groups so the launch
-                           * does not end in a tail of idle lanes, large jobs prefer 64 (fewer partials). */
+                           * does not end in a tail of idle lanes; large jobs prefer large groups (fewer partials), but at 64
+                           * a 1024 x 1024 x 1024 spp job split over eight GPUs ends in a tail worth 9 % of its time. */
   int row_begin, row_end; /* pixel-row shard [begin, end); row_end <= 0 means height */
   int row_step;           /* every row_step-th row of the shard, starting at row_begin (<= 1: every row).  Interleaved
                            * shards (begin = rank, step = world) balance the load across GPUs; outputs are compact */

@@ -461,7 +461,7 @@ int make_plan(const SceneHandle* h, const IptRenderParams* p, Plan* plan) {
   rp.c_diff = (1.0f / 0.318309873f) / p->p_rr;   // canon v2: diffuse coeff = cos * ((1 / (1/pi)) / p_rr), path_trace.cu:137
   int gs = p->group_samples;
   if (gs < 0) {   // auto (include/ipt_b200.h): depends on the full image size only
-    gs = 64;
+    gs = 32;   // cap 32, not 64: the bench job as one of eight row shards runs 21.3 instead of 23.5 ms (tail of 1.3 ms work items), whole: +0.75 % (profiles/r02_group_cap.txt)
     while (gs > 1 && (long long)p->width * p->height * p->spp < ((long long)gs << 22)) gs >>= 1;
   }
   rp.group_samples = (gs <= 0 || gs > p->spp) ? p->spp : gs;

@@ -1150,7 +1150,7 @@ static void render_sample(const Scene& sc, const Params& P, int r, int c, int sa
 static inline int group_size(const Params& P) {
   int gs = P.group_samples;
   if (gs < 0) {
-    gs = 64;
+    gs = 32;
     while (gs > 1 && (long long)P.width * P.height * P.spp < ((long long)gs << 22)) gs >>= 1;
   }
   return (gs <= 0 || gs > P.spp) ? P.spp : gs;
