@@ -37,7 +37,7 @@ if ROOT not in sys.path:
 ASSETS = os.path.join(ROOT, "tests", "golden", "assets")
 
 WORKLOAD = {"name": "CornellBox-Empty-CO forward path trace 1024x1024, 1024 spp, depth 8", "width": 1024, "height": 1024, "spp": 1024,
-            "max_depth": 8, "p_rr": 0.9, "group_samples": 64}
+            "max_depth": 8, "p_rr": 0.9, "group_samples": -1}   # -1: the library's size rule (32 for this job, include/ipt_b200.h)
 CORNELL = [{"pos": [0, 0, 4], "ori": [0, 0, 0], "scl": [2, 2, 2], "obj": "./CornellBox/CornellBox-Empty-CO.obj",
             "mtl": "./CornellBox/CornellBox-Empty-CO.mtl"}]
 FLOP_PER_TEST = 36   # denom 5 + numerator 6 + div 1 + point 6 + three edge planes 18
