@@ -72,6 +72,60 @@ def test_closest_hit_bit_exact(ipt, oracle, scene, mode):
     assert (tri_o >= 0).mean() > 0.5
 
 
+def slab_adversarial_rays(osc, seed=3):
+    """Rays against the traversal's box test (quantised records: plane distance = fma(2^23 + q, scale/d, (off - p)/d - 2^23 scale/d),
+    intersect.cuh): origins 10 .. 1e4 units away aimed at points on triangles (cancellation in (off - p)/d), directions exactly
+    parallel to an axis or with one / two components of 1e-4 .. 1e-30 (clamped reciprocals, huge plane distances), origins exactly on
+    triangle vertices and inside box face planes.
+
+    Known limit (found with this generator at 1e5 units, session r02_s28): the FP32 triangle test itself accepts a
+    hit whose t is off by ~2^-24 (|n.p| + |k|) / |n.d|; from 1e5 units away that is 0.008 along the ray, enough to accept a triangle the
+    ray misses by 3e-4 -- outside its padded box (pad 1e-5 (1 + |coordinate|)), so the traversal returns the next hit instead.  One of
+    39600 rays, identically for float, quantised and 4-wide node records: a property of fixed padding, not of the record format."""
+    tab = osc.triangle_table()
+    v = tab["verts"].astype(np.float64)
+    rng = np.random.RandomState(seed)
+    nT = v.shape[0]
+    rays = []
+    pick = rng.randint(0, nT, 600)
+    for i in pick:
+        w = rng.dirichlet([1, 1, 1])
+        q = w @ v[i]
+        for dist in (10.0, 1e2, 1e3, 1e4):
+            u = rng.normal(size=3)
+            u /= np.linalg.norm(u)
+            rays.append(np.concatenate([q - dist * u, u]))
+            k = rng.randint(3)                                   # approach along an axis, exactly and almost
+            e = np.zeros(3); e[k] = rng.choice([-1.0, 1.0])
+            rays.append(np.concatenate([q - dist * e, e]))
+            for tiny in (1e-4, 1e-7, 1e-12, 1e-30):
+                d = e.copy(); d[(k + 1) % 3] = tiny * rng.choice([-1, 1]); d[(k + 2) % 3] = tiny * rng.choice([-1, 0, 1])
+                d /= np.linalg.norm(d)
+                rays.append(np.concatenate([q - min(dist, 1e3) * d, d]))
+        for j in range(3):                                       # origins exactly on vertices, axis-parallel directions
+            for k in range(3):
+                for sgn in (-1.0, 1.0):
+                    e = np.zeros(3); e[k] = sgn
+                    rays.append(np.concatenate([v[i, j], e]))
+                    rays.append(np.concatenate([v[i, j] - 3.0 * e, e]))    # ... and running through the vertex from outside
+    return np.array(rays, np.float32)
+
+
+@pytest.mark.parametrize("scene,mode", [("cornell_sphere", 0), ("cornell_sphere", 2), ("rotated_cubes", 2)])
+def test_traversal_box_test_adversarial_rays(ipt, oracle, scene, mode):
+    """the BVH path must return the brute-force closest hit bit for bit whatever the box test does with far origins, axis-parallel
+    directions and origins on box faces (a conservative test may only visit more nodes)"""
+    objects = scene_objects(scene)
+    g, o = _pair(ipt, oracle, objects, traversal_mode=mode)
+    assert g.uses_bvh
+    rays = slab_adversarial_rays(o)
+    tri_g, t_g = g.trace(rays)
+    tri_o, t_o = o.trace(rays)
+    bad = np.nonzero((tri_g != tri_o) | (t_g.view(np.uint32) != t_o.view(np.uint32)))[0]
+    assert bad.size == 0, "first mismatches: %s" % [(int(b), rays[b].tolist(), int(tri_g[b]), int(tri_o[b]), float(t_g[b]), float(t_o[b])) for b in bad[:3]]
+    assert (tri_o >= 0).mean() > 0.5
+
+
 def test_trace_edge_cases(ipt, oracle):
     g, o = _pair(ipt, oracle, scene_objects("cornell"))
     tri, t = g.trace(np.zeros((0, 6), np.float32))

@@ -1,0 +1,11 @@
+#!/bin/bash
+# round-2 GPU session 28: adversarial rays (first version: distances up to 1e5) against the traversal's box test (far origins, axis-parallel directions, origins on vertices)
+# for all three node-record formats: shipped (quantised binary), IPT_BVH_QUANT=2 (4-wide), IPT_BVH_QUANT=0 (float)
+set -x
+O=gpurun_out/r02_s28; mkdir -p $O
+for v in shipped q4 float; do
+  lib=inverse_path_tracer_b200/lib/ab/$v.so; [ $v = shipped ] && lib=inverse_path_tracer_b200/lib/libipt_b200.so
+  echo "== $v" >> $O/adversarial.txt
+  IPT_B200_LIB=$PWD/$lib timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "adversarial or closest_hit or fuzz or large_triangle" 2>&1 | tail -8 >> $O/adversarial.txt
+done
+cat $O/adversarial.txt
