@@ -557,7 +557,10 @@ def config5_extra(args, ipt, native, torch, np, dev, peaks, peak_kind):
                                                   "peak_source": "%s HBM copy bandwidth (MEASURED_PEAKS.json)" % peak_kind,
                                                   "l2_resident_copy_gbs": native.measure_copy_gbps(32 << 20, 20),
                                                   "algorithmic": "%.1f child boxes x 32 B + %.2f leaf triangles x 64 B = %.0f bytes per ray (iptTraceRaysStatsDevice)" % (
-                                                      boxes_per_ray, tris_per_ray, bytes_per_ray)}}
+                                                      boxes_per_ray, tris_per_ray, bytes_per_ray),
+                                                  "note": "algorithmic = the reference's data structure (32-byte boxes, SURVEY.md 8d), as in round 1; the shipped traversal records "
+                                                          "hold a child box in 16 bytes and a leaf visit reads 16 B planes first, so the bytes actually requested are about "
+                                                          "%.0f per ray and `frac` overstates the share of the HBM peak this kernel moves" % (boxes_per_ray * 16 + tris_per_ray * 32)}}
     out["kernel_launches"] = int(L.iptKernelLaunchCount() - k0)
     sc.close()
     return out

@@ -194,7 +194,8 @@ def trace_test(a, sc, L):
     torch.cuda.synchronize()
     boxes_per_ray, tris_per_ray = float(stats[0]) / n, float(stats[1]) / n
     bytes_per_ray = boxes_per_ray * 32 + tris_per_ray * 64
-    print("traversal work per incoherent ray: %.1f child boxes (32 B) + %.2f leaf triangles (64 B) = %.0f algorithmic bytes" % (boxes_per_ray, tris_per_ray, bytes_per_ray))
+    print("traversal work per incoherent ray: %.1f child boxes (32 B) + %.2f leaf triangles (64 B) = %.0f algorithmic bytes (quantised records: 16 B per box requested)" % (
+        boxes_per_ray, tris_per_ray, bytes_per_ray))
     for rep in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
