@@ -34,6 +34,9 @@ constexpr int kFetchQuorum = IPT_FETCH_QUORUM;
 #ifndef IPT_TRACE_MINB
 #define IPT_TRACE_MINB 10   // resident blocks per SM the register allocation aims at (10: 48 registers, no spills; 12: 40 registers, 70 bytes of spills, 2 % slower; 16: 32 registers, 36 % slower)
 #endif
+#ifndef IPT_SPECULATE
+#define IPT_SPECULATE 0   // 1: a lane that reaches a leaf postpones it once and keeps descending (Aila & Laine's speculative traversal)
+#endif
 #ifndef IPT_RAY_CHUNK
 #define IPT_RAY_CHUNK 128
 #endif
@@ -58,14 +61,15 @@ __global__ void __launch_bounds__(kBlock, IPT_TRACE_MINB) k_trace_rays_bvh(DevSc
   r.best_t = INFINITY; r.best_i = -1; r.sp = 0;
   int idx = -1;
   bool exhausted = false;       // the batch has no ray left for this lane
+  int pend = 0;                 // IPT_SPECULATE: a postponed leaf (descriptor < 0), 0 = none
   int chunk_next = 0, chunk_end = 0;   // the warp's current chunk of ray indices (warp-uniform; a batch has < 2^31 rays)
   for (;;) {
     // ---- fetch ----
-    const bool want = r.cur == kBvhDone && !exhausted;
+    const bool want = r.cur == kBvhDone && pend == 0 && !exhausted;
     const unsigned wm = __ballot_sync(kFull, want);
     // a fetch costs the warp ~60 instructions however few lanes take part: wait for kFetchQuorum finished lanes unless
     // the others have nothing to do either
-    if (wm && (__popc(wm) >= kFetchQuorum || __ballot_sync(kFull, r.cur != kBvhDone) == 0u)) {
+    if (wm && (__popc(wm) >= kFetchQuorum || __ballot_sync(kFull, r.cur != kBvhDone || pend != 0) == 0u)) {
       if (want && idx >= 0) { tri[idx] = r.best_i; tout[idx] = r.best_t; idx = -1; }
       // rays are claimed from the global counter kRayChunk at a time per warp (one atomic per chunk, not per refill:
       // every warp of the grid hits the same address); a refill takes what is left of the warp's chunk first
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(kBlock, IPT_TRACE_MINB) k_trace_rays_bvh(DevSc
         }
       }
     }
-    if (__all_sync(kFull, r.cur == kBvhDone)) {
+    if (__all_sync(kFull, r.cur == kBvhDone && pend == 0)) {
       if (__all_sync(kFull, exhausted)) break;
       continue;   // lanes whose new ray ended at once (no ray / root box missed) store and refetch at the top
     }
@@ -117,22 +121,42 @@ __global__ void __launch_bounds__(kBlock, IPT_TRACE_MINB) k_trace_rays_bvh(DevSc
       if (im == 0u) break;
       if (__popc(im) < kInnerQuorum) {
         // leave only if the waiting lanes will then do something: a leaf to test, or enough finished lanes for a fetch
-        const unsigned leaves = __ballot_sync(kFull, r.cur < 0);
-        const unsigned idle = __ballot_sync(kFull, r.cur == kBvhDone && !exhausted);
+        const unsigned leaves = __ballot_sync(kFull, r.cur < 0 || (r.cur == kBvhDone && pend != 0));
+        const unsigned idle = __ballot_sync(kFull, r.cur == kBvhDone && pend == 0 && !exhausted);
         if (leaves != 0u || __popc(idle) >= kFetchQuorum) break;
       }
-      if (inner) bvh_step<STATS>(sc, r, col, stride, &nodes, &tris);
+      if (inner) {
+        bvh_step<STATS>(sc, r, col, stride, &nodes, &tris);
+#if IPT_SPECULATE
+        if (r.cur < 0 && pend == 0) {   // first leaf: postpone it, continue with the next stack entry
+          pend = r.cur;
+          r.sp -= 1;
+          r.cur = kBvhDone;
+          if (r.sp >= 0) r.cur = lds1i(col + (uint32_t)r.sp * stride);
+          r.sp = max(r.sp, 0);
+        }
+#endif
+      }
     }
     // ---- leaves ----
-    if (r.cur < 0) {
+    if (r.cur < 0 || pend != 0) {
       // the direction is only needed here (the inner phase runs on 1/d): re-read it instead of keeping three registers
-      // alive through the inner loop -- the kernel then fits 32 registers = 16 resident blocks per SM instead of 12
+      // alive through the inner loop
       const float2* r2 = reinterpret_cast<const float2*>(rays + 6 * (size_t)idx);
       const float2 b = __ldg(r2 + 1), c = __ldg(r2 + 2);
       r.d = mk3(b.y, c.x, c.y);
 #if IPT_BVH_QUANT
       const float2 a = __ldg(r2);   // quantised nodes: the inner phase runs on qa / qb, the origin is leaf-only as well
       r.p = mk3(a.x, a.y, b.x);
+#endif
+#if IPT_SPECULATE
+      if (pend != 0) {
+        const int packed = ~pend;
+        if (STATS) tris += (unsigned)(packed & 7);
+        test_leaf_lex(sc.geom, sc.geom_edges, sc.bvh_prims, packed >> 3, packed & 7, r.p, r.d, r.best_t, r.best_i);
+        pend = 0;
+      }
+      if (r.cur < 0)
 #endif
       bvh_step<STATS>(sc, r, col, stride, &nodes, &tris);
     }
