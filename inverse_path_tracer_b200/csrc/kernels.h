@@ -32,7 +32,7 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
                              int sm_count, int* host_live, unsigned long long* n_launches, cudaStream_t st, const WavefrontAdjoint* adj = nullptr);
 // one bounce of the wavefront integrator (trace.cu): closest hits of the rays [0, n) u [cap, cap + n), n = *n_live
 cudaError_t launch_trace_bounce(const DevScene& sc, const float* rays, const int* n_live, int cap, int* tri, float* t, unsigned long long* counter,
-                                int sm_count, unsigned long long* n_launches, cudaStream_t st);
+                                int sm_count, unsigned long long* n_launches, cudaStream_t st, bool seeded);
 cudaError_t launch_trace_rays(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter, int sm_count, cudaStream_t st);
 cudaError_t launch_trace_rays_stats(const DevScene& sc, const float* rays, int n, int* tri, float* t, unsigned long long* counter,
                                     unsigned long long* stats, int sm_count, cudaStream_t st);

@@ -217,10 +217,10 @@ static cudaError_t launch_trace_small(const DevScene& sc, const float* rays, int
 
 // one bounce of the wavefront integrator: hits of the rays [0, n) u [cap, cap + n), n = *n_live
 cudaError_t launch_trace_bounce(const DevScene& sc, const float* rays, const int* n_live, int cap, int* tri, float* t, unsigned long long* counter,
-                                int sm_count, unsigned long long* n_launches, cudaStream_t st) {
+                                int sm_count, unsigned long long* n_launches, cudaStream_t st, bool seeded) {
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
   if (e != cudaSuccess) return e;
-  if (sc.nGroups > 0) {
+  if (sc.nGroups > 0 && !seeded) {   // `seeded`: tri / t already hold the hits among the brute-force set (written by k_wf_shade)
     e = launch_trace_small(sc, rays, 0, n_live, cap, tri, t, sm_count, st);
     if (e != cudaSuccess) return e;
     *n_launches += 1;

@@ -79,7 +79,13 @@ __device__ __forceinline__ void wf_load_ray(const float* __restrict__ rays, size
 
 // camera rays of a batch (path_trace.cu:155-165): path i = ss * tile_n + pixel-in-tile, live slot i
 __global__ void __launch_bounds__(kWfBlock) k_wf_generate(DevScene sc, DevRender rp, WfBatch b, float4* __restrict__ state, float* __restrict__ rays,
-                                                          int* __restrict__ n_live, unsigned long long* __restrict__ counters) {
+                                                          int* __restrict__ hit_tri, float* __restrict__ hit_t, int* __restrict__ n_live,
+                                                          unsigned long long* __restrict__ counters) {
+  // like k_wf_shade, the kernel leaves the camera rays' hits among the scene's brute-force set for the traversal to start from
+  extern __shared__ float4 wf_smem[];
+  float4* wf_after;
+  const SmallScene ss = stage_small_scene(sc, wf_smem, &wf_after);
+  __syncthreads();
   const int n = b.tile_n * b.ns;
   const int cap = b.cap;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -100,6 +106,12 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(DevScene sc, DevRender
     state[5 * (size_t)cap + i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     wf_store_ray(rays, (size_t)i, rpos, rdir);
     wf_store_ray(rays, (size_t)cap + i, rpos, mk3(0.0f, 0.0f, 0.0f));
+    if (ss.nGroups > 0) {
+      HitRec he, hs;
+      closest_hit_small2(ss, rpos, rdir, rpos, mk3(0.0f, 0.0f, 0.0f), he, hs);
+      hit_tri[i] = he.tri; hit_t[i] = he.t;
+      hit_tri[(size_t)cap + i] = hs.tri; hit_t[(size_t)cap + i] = hs.t;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *n_live = n;
@@ -113,8 +125,17 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_generate(DevScene sc, DevRender
 template <bool PLAIN, bool RECORD>
 __global__ void __launch_bounds__(kWfBlock, PLAIN ? IPT_WF_MINB_PLAIN : IPT_WF_MINB) k_wf_shade(DevScene sc, DevRender rp, WfBatch b, int bounce, const float4* __restrict__ sin_, float4* __restrict__ sout,
                                                        const float* __restrict__ rin, float* __restrict__ rout, const int* __restrict__ hit_tri,
-                                                       const float* __restrict__ hit_t, const int* __restrict__ n_in, int* __restrict__ n_out,
+                                                       const float* __restrict__ hit_t, int* __restrict__ hit_tri_out, float* __restrict__ hit_t_out,
+                                                       const int* __restrict__ n_in, int* __restrict__ n_out,
                                                        float* __restrict__ lsamp, unsigned long long* __restrict__ counters, WfRecord rec) {
+  // the scene's brute-force set (whole small scene / large triangles of a BVH scene) in shared memory: the kernel tests the two
+  // rays it writes for a surviving path against it right away (the dual-ray loop of k_paths) and stores the hits where the next
+  // bounce's traversal picks them up as its starting bound -- the separate k_trace_rays pass per bounce (2.4 of 29 ms on the
+  // 5.2 M-triangle scene: a re-read of every ray and nine launches) is only left for the camera rays
+  extern __shared__ float4 wf_smem[];
+  float4* wf_after;
+  const SmallScene ss = stage_small_scene(sc, wf_smem, &wf_after);
+  __syncthreads();
   const int nT = sc.nT, nE = sc.nE;
   const size_t cap = (size_t)b.cap;
   const int n = *n_in;
@@ -301,6 +322,12 @@ __global__ void __launch_bounds__(kWfBlock, PLAIN ? IPT_WF_MINB_PLAIN : IPT_WF_M
         wf_store_ray(rout, cap + jn, sh_org, sh_valid ? sh_dir : zero3);
         n_ext += ext_valid ? 1u : 0u;
         n_shadow += sh_valid ? 1u : 0u;
+        if (ss.nGroups > 0) {
+          HitRec he, hs;
+          closest_hit_small2(ss, rpos, ext_valid ? rdir : zero3, sh_org, sh_valid ? sh_dir : zero3, he, hs);
+          hit_tri_out[jn] = he.tri; hit_t_out[jn] = he.t;
+          hit_tri_out[cap + jn] = hs.tri; hit_t_out[cap + jn] = hs.t;
+        }
       }
     }
   }
@@ -443,11 +470,11 @@ __global__ void __launch_bounds__(kWfBlock) k_wf_sweep(DevScene sc, WfBatch b, W
 
 // ---- wavefront forward pass ------------------------------------------------------------------------------
 // workspace layout (bytes, all 256-aligned): state A, state B (6 float4 x cap each), rays A, rays B
-// (2 x 6 floats x cap each), hit ids, hit t (2 x cap each), per-sample radiance (3 x cap), control words
+// (2 x 6 floats x cap each), hit ids A / B, hit t A / B (2 x cap each), per-sample radiance (3 x cap), control words
 static size_t wf_align(size_t b) { return (b + 255) & ~(size_t)255; }
 size_t wavefront_workspace_bytes(int cap) {
   const size_t c = (size_t)cap;
-  return 2 * wf_align(6 * c * sizeof(float4)) + 2 * wf_align(12 * c * sizeof(float)) + wf_align(2 * c * sizeof(int)) + wf_align(2 * c * sizeof(float)) +
+  return 2 * wf_align(6 * c * sizeof(float4)) + 2 * wf_align(12 * c * sizeof(float)) + 2 * wf_align(2 * c * sizeof(int)) + 2 * wf_align(2 * c * sizeof(float)) +
          wf_align(3 * c * sizeof(float)) + 256;
 }
 // vertex record of the adjoint replay: vdepth bounces x cap paths x vf4 float4, plus the path lengths
@@ -463,8 +490,12 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
   state[1] = (float4*)w; w += wf_align(6 * c * sizeof(float4));
   rays[0] = (float*)w; w += wf_align(12 * c * sizeof(float));
   rays[1] = (float*)w; w += wf_align(12 * c * sizeof(float));
-  int* hit_tri = (int*)w; w += wf_align(2 * c * sizeof(int));
-  float* hit_t = (float*)w; w += wf_align(2 * c * sizeof(float));
+  int* hit_tri[2];
+  float* hit_t[2];
+  hit_tri[0] = (int*)w; w += wf_align(2 * c * sizeof(int));
+  hit_tri[1] = (int*)w; w += wf_align(2 * c * sizeof(int));
+  hit_t[0] = (float*)w; w += wf_align(2 * c * sizeof(float));
+  hit_t[1] = (float*)w; w += wf_align(2 * c * sizeof(float));
   float* lsamp = (float*)w; w += wf_align(3 * c * sizeof(float));
   unsigned long long* trace_counter = (unsigned long long*)w;   // [0]
   int* n_live = (int*)(w + 16);                                 // [0], [1]: ping-pong live counts
@@ -480,6 +511,11 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
 
   // the four variants of the shading kernel: scenes without a Phong lobe / vertex normals (PLAIN), with the adjoint's vertex record
   auto shade = sc.plain ? (adj ? k_wf_shade<true, true> : k_wf_shade<true, false>) : (adj ? k_wf_shade<false, true> : k_wf_shade<false, false>);
+  const size_t shade_smem = small_scene_smem_bytes(sc.nStream);
+  e = cudaFuncSetAttribute((const void*)shade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(k_wf_generate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem);
+  if (e != cudaSuccess) return e;
   const int tile_cap = std::min(rp.n_pix, cap);
   const bool unbounded = rp.max_depth <= 0;
   for (int p0 = 0; p0 < rp.n_pix; p0 += tile_cap) {
@@ -493,7 +529,8 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
         int cur = 0;
         {
           NvtxRange r("ipt.wavefront.generate");
-          k_wf_generate<<<std::min((n_paths + kWfBlock - 1) / kWfBlock, shade_grid), kWfBlock, 0, st>>>(sc, rp, b, state[0], rays[0], n_live + 0, counters);
+          k_wf_generate<<<std::min((n_paths + kWfBlock - 1) / kWfBlock, shade_grid), kWfBlock, shade_smem, st>>>(sc, rp, b, state[0], rays[0], hit_tri[0], hit_t[0],
+                                                                                                                 n_live + 0, counters);
         }
         *n_launches += 1;
         for (int bounce = 0;; bounce++) {
@@ -502,13 +539,14 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevRender& rp, void* work
           if (e != cudaSuccess) return e;
           {
             NvtxRange r("ipt.wavefront.extend");
-            e = launch_trace_bounce(sc, rays[cur], n_live + cur, cap, hit_tri, hit_t, trace_counter, sm_count, n_launches, st);
+            // the kernel that wrote the rays (k_wf_generate / k_wf_shade) has left their hits among the brute-force set
+            e = launch_trace_bounce(sc, rays[cur], n_live + cur, cap, hit_tri[cur], hit_t[cur], trace_counter, sm_count, n_launches, st, true);
           }
           if (e != cudaSuccess) return e;
           {
             NvtxRange r("ipt.wavefront.shade");
-            shade<<<shade_grid, kWfBlock, 0, st>>>(sc, rp, b, bounce, state[cur], state[cur ^ 1], rays[cur], rays[cur ^ 1], hit_tri, hit_t, n_live + cur,
-                                                   n_live + (cur ^ 1), lsamp, counters, rec);
+            shade<<<shade_grid, kWfBlock, shade_smem, st>>>(sc, rp, b, bounce, state[cur], state[cur ^ 1], rays[cur], rays[cur ^ 1], hit_tri[cur], hit_t[cur],
+                                                            hit_tri[cur ^ 1], hit_t[cur ^ 1], n_live + cur, n_live + (cur ^ 1), lsamp, counters, rec);
           }
           *n_launches += 1;
           cur ^= 1;
