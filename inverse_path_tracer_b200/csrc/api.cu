@@ -417,11 +417,16 @@ static int upload_scene(SceneHandle* h) {
     h->bvh_root_desc = nodes.empty() ? 0 : desc_of(0);
     h->bvh_depth = max_depth;
     h->n_nodes = (int)nodes.size();
-    IPT_CUDA(cudaMalloc(&h->bvh_wide, std::max<size_t>(wide.size(), 4) * sizeof(float4)));
+#if IPT_BVH_QUANT
+    const size_t n_wide_dev = 4;   // the float traversal records are not used by this build (device_scene.h): keep a token allocation
+#else
+    const size_t n_wide_dev = std::max<size_t>(wide.size(), 4);
+#endif
+    IPT_CUDA(cudaMalloc(&h->bvh_wide, n_wide_dev * sizeof(float4)));
     IPT_CUDA(cudaMalloc(&h->bvh_nodes, std::max<size_t>(packed.size(), 2) * sizeof(float4)));
     IPT_CUDA(cudaMalloc(&h->bvh_prims, std::max<size_t>(perm.size(), 1) * sizeof(int)));
     if (!nodes.empty()) {
-      IPT_CUDA(cudaMemcpy(h->bvh_wide, wide.data(), wide.size() * sizeof(float4), cudaMemcpyHostToDevice));
+      IPT_CUDA(cudaMemcpy(h->bvh_wide, wide.data(), std::min(n_wide_dev, wide.size()) * sizeof(float4), cudaMemcpyHostToDevice));
       IPT_CUDA(cudaMemcpy(h->bvh_nodes, packed.data(), packed.size() * sizeof(float4), cudaMemcpyHostToDevice));
       IPT_CUDA(cudaMemcpy(h->bvh_prims, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice));
       // leaf triangles are read in tree order: store their records that way (slot j = triangle perm[j]), so a leaf is
