@@ -63,6 +63,43 @@ def test_inverse_step_equals_python_adam_loop(ipt):
     b.close()
 
 
+def test_inverse_step_on_bvh_scene_equals_python_adam_loop(ipt):
+    """the same equality on a scene that runs through the BVH / wavefront path (Cornell box + sphere mesh with vertex normals,
+    1298 triangles): iptInverseStep's BVH branch (forward without resolve, k_resolve_loss, wavefront adjoint) against render_loss +
+    torch Adam on a second handle"""
+    import torch
+    from conftest import scene_objects
+    from inverse_path_tracer_b200.torch_api import TorchScene, inverse_optimizer, render_loss
+    W, H, SPP, STEPS = 48, 40, 8, 4
+    target = _target(torch, W, H, seed=2)
+    a = TorchScene(scene_objects("cornell_sphere"), asset_root=ASSETS)
+    b = TorchScene(scene_objects("cornell_sphere"), asset_root=ASSETS)
+    assert a.scene.uses_bvh
+    kd0 = np.full((a.nT, 3), 0.6, np.float32)
+    opt = inverse_optimizer(a, ipt.default_params(width=W, height=H, spp=SPP, max_depth=6, seed=0), target, lr=0.02)
+    opt.set_kd(kd0)
+    opt.step(40, STEPS)
+    loss_lib, kd_lib, steps, hist = opt.state(history=STEPS)
+    assert steps == STEPS
+    kd = torch.full((b.nT, 3), 0.6, device="cuda", requires_grad=True)
+    adam = torch.optim.Adam([kd], lr=0.02)
+    losses = []
+    for i in range(STEPS):
+        adam.zero_grad(set_to_none=True)
+        loss = render_loss(kd, b, ipt.default_params(width=W, height=H, spp=SPP, max_depth=6, seed=40 + i), target, reduce=False)
+        loss.backward()
+        adam.step()
+        with torch.no_grad():
+            kd.clamp_(1e-3, 1.0)
+        losses.append(float(loss.detach()))
+    assert abs(hist[0] - losses[0]) <= 1e-6 * abs(losses[0])
+    assert np.abs(kd_lib - kd.detach().cpu().numpy()).max() < 2e-5
+    assert abs(loss_lib - losses[-1]) <= 1e-4 * abs(losses[-1])
+    opt.close()
+    a.close()
+    b.close()
+
+
 def test_inverse_two_ranks_exchange_on_one_gpu(ipt):
     """two optimisers (rank 0 / 1 of world 2, interleaved row shards) in one process on one GPU, mailboxes connected by
     raw pointers: the exchange protocol of k_inverse_update must deliver the same albedos to both and match one rank
