@@ -357,6 +357,41 @@ def b200_arm(args):
         he_dt = max_over_ranks(time.perf_counter() - t0)
         point["e2e"] = {"value": sum_over_ranks(he_rays) / he_dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(nT * 3 * 4),
                         "d2h_bytes_per_step": int(hrows * 512 * 3 * 4 + 24), "steps": 20, "ms_per_frame": 1e3 * he_dt / 20}
+        if world == 1:
+            # the same frames as a stream of work: two scene handles on two CUDA streams (include/ipt_b200.h "Concurrency": one
+            # handle per stream), frames alternating, one event pair around all of them -- the tail of one frame's persistent
+            # launch (its longest paths; unbounded depth) overlaps the start of the next frame on the other stream
+            ts_b = TorchScene(CORNELL, asset_root=ASSETS, device=local)
+            sts = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+            scs, outs2 = [ts, ts_b], [hout, torch.empty_like(hout)]
+            cn2 = [torch.zeros_like(counters), torch.zeros_like(counters)]
+            tot2 = [torch.zeros_like(total), torch.zeros_like(total)]
+            for k in range(2):
+                with torch.cuda.stream(sts[k]):
+                    scs[k].render(hp(200 + k), out=outs2[k], counters=cn2[k])
+            torch.cuda.synchronize()
+            flush.zero_()
+            torch.cuda.synchronize()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            for st_ in sts:
+                st_.wait_stream(torch.cuda.current_stream())
+            for i in range(reps):
+                k = i & 1
+                with torch.cuda.stream(sts[k]):
+                    scs[k].render(hp(i), out=outs2[k], counters=cn2[k])
+                    tot2[k].add_(cn2[k])
+            for st_ in sts:
+                torch.cuda.current_stream().wait_stream(st_)
+            eb.record()
+            torch.cuda.synchronize()
+            ms2 = ea.elapsed_time(eb)
+            c2 = [int(x) for x in (tot2[0] + tot2[1]).tolist()]
+            point["two_handles_two_streams"] = {"mrays_per_s": (c2[1] + c2[2]) / (ms2 * 1e-3) / 1e6, "mpaths_per_s": c2[0] / (ms2 * 1e-3) / 1e6,
+                                                "ms_per_frame": ms2 / reps,
+                                                "timing": "one CUDA-event interval around %d frames issued alternately on two scene handles / two streams "
+                                                          "(throughput of a stream of frames, not the latency of one; no L2 flush inside: the scene lives in shared memory)" % reps}
+            ts_b.close()
         extra["metric_point_cornell_512x512_64spp_unbounded"] = point
 
         # ---- inverse iterations/s (BASELINE config 3): scenes/0.txt, 500x500 target, 64 spp / iteration, Adam on the 30x3
