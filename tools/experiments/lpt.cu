@@ -1,3 +1,7 @@
+// NOT PART OF THE LIBRARY.  Kept as the record of an experiment (profiles/r02_small_launches.txt): built as csrc/lpt.cu with a
+// DevOut::item_order indirection in k_paths' work claim, measured on a B200 (sessions r02_s36 / r02_s37), found not to help, removed.
+// It compiles only next to csrc/device_scene.h and csrc/kernels.h (with launch_item_order / item_order_bytes declared there).
+//
 // lpt.cu -- longest paths first: the order in which k_paths hands out the work items of a small launch
 //
 // A persistent launch ends in a tail as long as its longest path.  With Russian roulette and no depth limit (the reference,
