@@ -24,7 +24,7 @@ namespace ipt {
 // Ray index space: `n_live == nullptr`: rays [0, n).  Otherwise (wavefront): n = *n_live and the batch is
 // [0, n) u [cap, cap + n).  A ray with direction 0 is "no ray": a miss.
 #ifndef IPT_INNER_QUORUM
-#define IPT_INNER_QUORUM 10
+#define IPT_INNER_QUORUM 14
 #endif
 constexpr int kInnerQuorum = IPT_INNER_QUORUM;
 #ifndef IPT_FETCH_QUORUM
