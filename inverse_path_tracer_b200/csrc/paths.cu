@@ -58,6 +58,12 @@ constexpr uint32_t kRingStride = kBlock * 16u;   // bytes between two slots of o
 // PLAIN is a compile-time promise that no triangle has per-vertex normals or a specular lobe (true for every
 // asset the reference ships); the Phong / vertex-normal code is then not compiled into the kernel at all.
 // A/B switches of round 2 (profiles/r02_ab.txt): 1 = the shipped choice
+#ifndef IPT_EXPERIMENT_FAST_SINCOS
+#define IPT_EXPERIMENT_FAST_SINCOS 0
+#endif
+#ifndef IPT_EXPERIMENT_NO_ND_NORMALIZE
+#define IPT_EXPERIMENT_NO_ND_NORMALIZE 0
+#endif
 #ifndef IPT_FASTMATH
 #define IPT_FASTMATH 1        // sqrt / normalise through the single-test sequences of ipt_math.cuh (same bits as sqrtf and /)
 #endif
@@ -448,7 +454,11 @@ __global__ void __launch_bounds__(kBlock, (MODE != MODE_GRAD && !BVH && PLAIN) ?
             // sampleNextDir (path_trace.cu:91-109), diffuse: the rotation FromTwoVectors(z, n) is fixed per
             // triangle and was built at load with the same arithmetic
             float sphi, cphi;
+#if IPT_EXPERIMENT_FAST_SINCOS   // measurement only: what a cheaper sin/cos(2 pi u) could buy (not the canon: MUFU approximations)
+            __sincosf(6.283185307179586f * u01(rn.z), &sphi, &cphi);
+#else
             sincos2pi(u01(rn.z), &sphi, &cphi);
+#endif
             const float ut = u01(rn.w);
             const float cth = IPT_SQRT_UNIT(ut), sth = IPT_SQRT(1.0f - ut);   // ut in [2^-33, 1]; 1 - ut may be 0
             const f3 hemi = mk3(sth * cphi, sth * sphi, cth);
@@ -458,7 +468,9 @@ __global__ void __launch_bounds__(kBlock, (MODE != MODE_GRAD && !BVH && PLAIN) ?
               const float4 r0 = M(5, tri), r1 = M(6, tri), r2 = M(7, tri);
               nd = mk3(dot3(r0.x, r0.y, r0.z, hemi), dot3(r1.x, r1.y, r1.z, hemi), dot3(r2.x, r2.y, r2.z, hemi));
             }
+#if !IPT_EXPERIMENT_NO_ND_NORMALIZE   // measurement only: the rotated hemisphere direction is unit length up to rounding; the canon normalises it
             nd = IPT_NORMALIZE(nd);
+#endif
           }
           const float cosn = dot3(nd, ns);
           if (MODE == MODE_GRAPH) {
