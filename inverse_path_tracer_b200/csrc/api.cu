@@ -43,9 +43,12 @@ static std::set<void*> g_registry;
 
 constexpr int kBruteForceMaxTris = 128;
 #ifndef IPT_LEAF_SIZE
-#define IPT_LEAF_SIZE 4
+#define IPT_LEAF_SIZE 2
 #endif
-constexpr int kTraversalLeafSize = IPT_LEAF_SIZE;   // leaf size of the internal triangle tree (<= 7: three bits in a descriptor); 4 is the reference's rule
+// leaf size of the internal triangle tree (<= 7: three bits in a descriptor).  The reference's rule is 4 (bvh.h:112, kept by iptBuildBVH);
+// on the 5.2 M-triangle scene (frame ms | incoherent Grays/s, profiles/r02_config5.txt): 1: 27.9 | 5.2, 2: 26.3 | 5.5, 3: 26.5 | 5.4,
+// 4: 26.9 | 5.3, 6: 28.6 | 4.8, 7: 29.3 | 4.7
+constexpr int kTraversalLeafSize = IPT_LEAF_SIZE;
 constexpr double kBigTriangleDiag = 0.25;   // a triangle is "large" when its box diagonal exceeds this fraction of the scene's
 static thread_local int g_big_max = 128;    // at most this many large triangles leave the tree (0: none)
 
