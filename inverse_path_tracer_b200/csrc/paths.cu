@@ -49,7 +49,13 @@ __device__ __forceinline__ int adj_light(const AdjVertex& v) { return __float_as
 // when a lane that needs a ray finds its ring empty, ALL lanes with a free slot generate one (so generation runs once per
 // ~2.4 trips at ~22 lanes) and taking a ray is one 16-byte load.  Entry = {direction, work item}; the generator's own
 // cursor (pixel, row / column, next sample, end) lives in two more shared-memory slots of the lane.
-constexpr int kRing = 4;
+#ifndef IPT_RING
+#define IPT_RING 4       // camera rays a lane keeps ready (power of two)
+#endif
+#ifndef IPT_CLAIM_MAX
+#define IPT_CLAIM_MAX 8  // longest run of work items a lane claims at once
+#endif
+constexpr int kRing = IPT_RING;
 constexpr int kRingF4 = kRing + 3;   // + two generator slots + the lane's item slot {partial sum rgb, work item}
 constexpr int kRingWords = kRingF4 * 4 + 1;   // 32-bit words per thread: the float4 slots + one word (last claim position)
 constexpr uint32_t kRingStride = kBlock * 16u;   // bytes between two slots of one thread
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(kBlock, (MODE != MODE_GRAD && !BVH && PLAIN) ?
       const int leader = __ffs(fm) - 1;
       const unsigned claim_base = (unsigned)__shfl_sync(kFull, lds1i(claim_a), leader);   // warp-uniform n: the leader's view
       const unsigned remaining = n_items > claim_base ? n_items - claim_base : 0u;
-      const unsigned n = min(max(remaining / (gridDim.x * blockDim.x * 2u), 1u), 8u);
+      const unsigned n = min(max(remaining / (gridDim.x * blockDim.x * 2u), 1u), (unsigned)IPT_CLAIM_MAX);
       unsigned base = 0;
       if ((int)lane == leader) base = atomicAdd(out.work_counter, (unsigned)__popc(fm) * n);   // overshoot <= 8 per lane: no wrap (make_plan)
       base = __shfl_sync(kFull, base, leader);
