@@ -49,8 +49,9 @@ __global__ void __launch_bounds__(kBlock, IPT_TRACE_MINB) k_trace_rays_bvh(DevSc
   extern __shared__ float4 smem[];
   const uint32_t col = smem_addr(reinterpret_cast<int*>(smem) + threadIdx.x), stride = blockDim.x * (uint32_t)sizeof(int);
   const unsigned lane = threadIdx.x & 31u;
-  // a scene with a brute-force set (large triangles kept out of the tree): k_trace_rays has already written each
-  // ray's hit among those into tri / tout; the traversal starts from that bound
+  // a scene with a brute-force set (large triangles kept out of the tree): each ray's hit among those is already in tri / tout
+  // -- written by k_trace_rays (iptTraceRays*) or by the wavefront kernel that produced the ray (k_wf_generate / k_wf_shade) --
+  // and the traversal starts from that bound
   const bool seeded = sc.nGroups > 0;
   // a batch has < 2^31 rays (a wavefront bounce: 2 x cap <= 2^25), so ray indices are ints
   const int n = n_live ? *n_live : n_direct;

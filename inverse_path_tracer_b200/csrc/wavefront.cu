@@ -23,7 +23,8 @@ namespace ipt {
 //     S0 = {multiplier, path index in batch}   S1 = {prevMultiplier, flags}     S2 = {L, cos(theta) of the shadow ray}
 //     S3 = {L_e, p_t of the sampled light}      S4 = {L_d, sampled light id}     S5 = {BSDF(direct) of the bounce, -}
 //   rays[6 * j] extension ray, rays[6 * (cap + j)] shadow ray of the previous bounce (direction 0 = no ray)
-//   hits likewise at j and cap + j.
+//   hits likewise at j and cap + j; the kernel that writes a ray also writes its hit among the scene's brute-force set there
+//   (two hit buffers, swapped with the rays), and k_trace_rays_bvh continues from it.
 // ------------------------------------------------------------------------------------------------
 enum { WF_END_AFTER = 1, WF_SH_VALID = 2, WF_EXT_VALID = 4 };
 #ifndef IPT_WF_BLOCK
